@@ -1,0 +1,135 @@
+"""CPU tests: the C oracle against the committed golden vectors (minted by the independent
+NumPy restatement), the two restatements against each other, and the wavefront-order proof."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle.np_oracle import NpSim
+from oracle.oracle import OracleSim, frac_to_threshold
+from tests.helpers import DT, GOLDEN, bits_equal, first_mismatch, load_golden, sim_kwargs
+
+CASES = ["bench_100x100", "term_80x48_disc", "term_48x42_random_gravity", "adversarial_64x40",
+         "odd_37x23", "default_2x2", "thin_3x64"]
+
+
+def _digest(o):
+    h = hashlib.sha256()
+    for a in (o.u, o.v, o.p, o.s):
+        h.update(np.ascontiguousarray(a, np.float32).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_c_oracle_reproduces_golden(name):
+    z, prm = load_golden(name)
+    o = OracleSim(prm["W"], prm["H"], **sim_kwargs(prm))
+    o.m[:] = z["mask"]
+    o.u[:], o.v[:], o.s[:] = z["u0"], z["v0"], z["s0"]
+    for st in range(1, prm["steps"] + 1):
+        o.step(prm["dt"])
+        assert _digest(o) == prm["hashes"][st - 1], f"{name}: step {st} digest differs"
+        if st in prm["keep"]:
+            for f in "uvps":
+                assert bits_equal(getattr(o, f), z[f"{f}_step{st}"]), \
+                    f"{name} {f} step {st}: " + first_mismatch(getattr(o, f), z[f"{f}_step{st}"], prm["H"])
+
+
+def test_edit_path_golden():
+    z = np.load(os.path.join(GOLDEN, "edit_path.npz"))
+    o = OracleSim(20, 10)
+    rng = np.random.default_rng(2)
+    for _ in range(30):
+        o.set_block(int(rng.integers(0, 20)), int(rng.integers(0, 10)))
+    o.step(DT)
+    o.resize(16, 12)
+    assert np.array_equal(o.m, z["m_after_resize"])
+    o.step(DT)
+    o.set_config(0.5, 20.0, 0.5, 900.0)
+    assert bits_equal(o.u, z["u_after_cfg"]) and bits_equal(o.s, z["s_after_cfg"])
+    o.step(DT)
+    for f in "uvps":
+        assert bits_equal(getattr(o, f), z[f + "_after"])
+    o.restart_sim()
+    assert np.array_equal(o.m, z["m_after_restart"])
+    assert bits_equal(o.u, z["u_after_restart"]) and bits_equal(o.s, z["s_after_restart"])
+
+
+@pytest.mark.parametrize("W,H,K,g", [(13, 9, 7, 0.0), (20, 31, 12, 9.8), (9, 40, 5, -3.0)])
+def test_wavefront_order_equals_lexicographic(W, H, K, g):
+    """sweeping by t = i + j + 2k is bit-identical to the reference's
+    lexicographic sweep.  NumPy literal triple loop vs NumPy wavefront vs C oracle."""
+    rng = np.random.default_rng(W * H)
+    a = NpSim(W, H, gravity=g, iterations=K)
+    b = NpSim(W, H, gravity=g, iterations=K)
+    c = OracleSim(W, H, gravity=g, iterations=K)
+    for _ in range(W * H // 7):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        a.set_block(x, y), b.set_block(x, y), c.set_block(x, y)
+    for _ in range(3):
+        a.step(DT, lexicographic=True)
+        b.step(DT)
+        c.step(DT)
+        for f in "uvps":
+            assert bits_equal(getattr(a, f), getattr(b, f)), f
+            assert bits_equal(getattr(a, f), getattr(c, f)), f
+
+
+def test_default_2x2_is_noop():
+    o = OracleSim(2, 2)
+    u0, s0 = o.u.copy(), o.s.copy()
+    o.step(DT)
+    assert bits_equal(o.u, u0) and bits_equal(o.s, s0)
+
+
+def test_initial_state_matches_reference_constants():
+    o = OracleSim(100, 100)
+    H = 100
+    assert np.all(o.u[H:2 * H] == 50.0) and np.all(o.u[:H] == 0) and np.all(o.u[2 * H:] == 0)
+    assert np.all(o.m[:H] == 1) and np.all(o.m[H:] == 0)
+    s = o.s
+    assert np.all(s[37:62] == 0.0) and np.all(s[:37] == 1.0) and np.all(s[62:] == 1.0)  # rows 37..62 (SURVEY a-7)
+
+
+def test_set_block_out_of_range_panics_like_reference():
+    o = OracleSim(8, 8)
+    with pytest.raises(IndexError):
+        o.set_block(8, 0)
+
+
+def test_zero_dt_gives_nonfinite_pressure_only():
+    o = OracleSim(16, 16)
+    o.step(0.0)
+    assert np.all(np.isfinite(o.u)) and np.all(np.isfinite(o.v))
+    assert not np.all(np.isfinite(o.p))  # pc = density / 0 = inf (SURVEY a-11)
+
+
+def test_cell_flags_and_scenes_are_deterministic():
+    o = OracleSim(64, 48)
+    o.scene_disc(20, 24, 6)
+    o.scene_random(0x5EED, 0.02)
+    f = o.cell_flags()
+    m = o.m.reshape(64, 48)
+    assert f.reshape(64, 48)[0].max() == 0 and f.reshape(64, 48)[:, 0].max() == 0
+    i, j = 10, 10
+    if not m[i, j]:
+        exp = 16 | (1 * (not m[i - 1, j])) | (2 * (not m[i + 1, j])) | (4 * (not m[i, j - 1])) | (8 * (not m[i, j + 1]))
+        assert f[i * 48 + j] == exp
+    assert frac_to_threshold(0.02) == (2 << 64) // 100
+    o2 = OracleSim(64, 48)
+    o2.scene_disc(20, 24, 6)
+    o2.scene_random(0x5EED, 0.02)
+    assert np.array_equal(o.m, o2.m)
+
+
+def test_redblack_variant_converges_to_same_flow_class():
+    """The red-black ordering is a different iteration, not the reference's; it must stay
+    within a loose tolerance of the lexicographic result on a smooth case."""
+    a = OracleSim(64, 64, iterations=50, mode=0)
+    b = OracleSim(64, 64, iterations=50, mode=1)
+    for _ in range(5):
+        a.step(DT)
+        b.step(DT)
+    assert np.max(np.abs(a.u - b.u)) < 0.25 * 50.0
+    assert abs(a.divergence_linf() - b.divergence_linf()) < 50.0
