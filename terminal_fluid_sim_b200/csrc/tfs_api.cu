@@ -1,0 +1,844 @@
+// tfs_api.cu -- the C ABI of libtfs_cuda.so (include/tfs.h) and the host-side step driver.
+// Single translation unit: kernels are in the .cuh files included below.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/tfs.h"
+#include "tfs_kernels.cuh"
+#include "tfs_systolic.cuh"
+
+#define TFS_VERSION_STRING "tfs-cuda 0.1.0 (sm_100a)"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+    } while (0)
+
+#define NEED(cond, code, msg) \
+    do {                      \
+        if (!(cond)) return fail(code, "%s", msg); \
+    } while (0)
+
+constexpr int kMaxProfSteps = 256;
+
+}  // namespace
+
+struct tfs_sim {
+    int device = 0;
+    size_t W = 0, H = 0;
+    tfs_config cfg{};
+    tfs_options opt{};
+    cudaStream_t stream = nullptr;
+    // fields; *2 are the alternates (advection double buffers, projection ping-pong)
+    float *u = nullptr, *v = nullptr, *p = nullptr, *s = nullptr;
+    float *u2 = nullptr, *v2 = nullptr, *p2 = nullptr, *s2 = nullptr;
+    uint8_t *m = nullptr, *flags = nullptr;
+    size_t cap = 0;  // allocated cells per array
+    bool flags_dirty = true;
+    // scratch
+    float *d_part = nullptr;  // reduction partials
+    float *h_pin = nullptr;   // pinned, 16 floats
+    void *d_stage = nullptr;  // view packing
+    size_t stage_bytes = 0;
+    tfs::SystolicWorkspace sys;
+    // measurement
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profiling = false;
+    cudaEvent_t prof_ev[kMaxProfSteps][4];
+    int prof_n = 0;
+    bool prof_created = false;
+    double acc_ms[3] = {0, 0, 0};
+    uint64_t acc_steps = 0;
+    uint64_t launches = 0;
+
+    tfs::Grid grid() const { return tfs::Grid{(long long)W, (long long)H, 0, (long long)W}; }
+    long long n() const { return (long long)W * (long long)H; }
+};
+
+namespace {
+
+inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int set_device(const tfs_sim *s) {
+    CU(cudaSetDevice(s->device));
+    return TFS_OK;
+}
+
+void free_fields(tfs_sim *s) {
+    float **fp[] = {&s->u, &s->v, &s->p, &s->s, &s->u2, &s->v2, &s->p2, &s->s2};
+    for (auto f : fp) {
+        if (*f) cudaFree(*f);
+        *f = nullptr;
+    }
+    if (s->m) cudaFree(s->m);
+    if (s->flags) cudaFree(s->flags);
+    s->m = s->flags = nullptr;
+    s->cap = 0;
+}
+
+// allocate all arrays for `cells` cells (+ one padding column worth so vector tails are safe)
+int alloc_fields(tfs_sim *s, size_t cells) {
+    free_fields(s);
+    size_t padded = cells + 64;
+    float **fp[] = {&s->u, &s->v, &s->p, &s->s, &s->u2, &s->v2, &s->p2, &s->s2};
+    for (auto f : fp) CU(cudaMalloc((void **)f, padded * sizeof(float)));
+    CU(cudaMalloc((void **)&s->m, padded));
+    CU(cudaMalloc((void **)&s->flags, padded));
+    CU(cudaMemsetAsync(s->m, 0, padded, s->stream));
+    CU(cudaMemsetAsync(s->flags, 0, padded, s->stream));
+    s->cap = cells;
+    return TFS_OK;
+}
+
+// Rust `f32 as usize` (saturating, NaN -> 0)
+size_t f32_as_usize(float x) {
+    if (!(x > 0.0f)) return 0;
+    if (x >= 18446744073709551616.0f) return SIZE_MAX;
+    return (size_t)x;
+}
+
+// set_horizontal_speed (simulator.rs:79-85) and set_smoke_pipe (:94-111) on the device copy
+int apply_wind_and_pipe(tfs_sim *s) {
+    const long long H = (long long)s->H, n = s->n();
+    tfs::Grid g = s->grid();
+    long long lo = H, hi = std::min(2 * H, n);
+    if (hi > lo) {
+        tfs::k_fill_range_f32<<<blocks_for(hi - lo, 256), 256, 0, s->stream>>>(s->u, g, lo, hi, s->cfg.wind_speed);
+        s->launches++;
+    }
+    hi = std::min(H, n);
+    tfs::k_fill_range_f32<<<blocks_for(hi, 256), 256, 0, s->stream>>>(s->s, g, 0, hi, 1.0f);
+    s->launches++;
+    const float pipe_height = (float)s->H * s->cfg.smoke_size;  // :101
+    const float middle = (float)s->H * 0.5f;                    // :102
+    long long mn = (long long)std::min<size_t>(f32_as_usize(middle - pipe_height * 0.5f), (size_t)n);
+    long long mx = (long long)std::min<size_t>(f32_as_usize(middle + pipe_height * 0.5f), (size_t)n);
+    if (mx > mn) {
+        tfs::k_fill_range_f32<<<blocks_for(mx - mn, 256), 256, 0, s->stream>>>(s->s, g, mn, mx, 0.0f);
+        s->launches++;
+    }
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+// create_horizontal_speed / create_smoke_pipe / zeroed v, p (simulator.rs:31-34, :44-48)
+int reset_fields(tfs_sim *s) {
+    const long long n = s->n();
+    const unsigned gb = std::min<unsigned>(blocks_for(n, 256), 148 * 16);
+    tfs::k_fill_f32<<<gb, 256, 0, s->stream>>>(s->u, n, 0.0f);
+    tfs::k_fill_f32<<<gb, 256, 0, s->stream>>>(s->v, n, 0.0f);
+    tfs::k_fill_f32<<<gb, 256, 0, s->stream>>>(s->p, n, 0.0f);
+    tfs::k_fill_f32<<<gb, 256, 0, s->stream>>>(s->s, n, 1.0f);
+    s->launches += 4;
+    CU(cudaGetLastError());
+    return apply_wind_and_pipe(s);
+}
+
+int refresh_flags(tfs_sim *s) {
+    if (!s->flags_dirty) return TFS_OK;
+    tfs::Grid g = s->grid();
+    tfs::k_cell_flags<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->flags, g, 0, (long long)s->W);
+    s->launches++;
+    CU(cudaGetLastError());
+    s->flags_dirty = false;
+    return TFS_OK;
+}
+
+int check_options(const tfs_options *o) {
+    NEED(o->iterations >= 0, TFS_ERR_INVALID_ARG, "options.iterations must be >= 0");
+    NEED(o->mode == TFS_MODE_WAVEFRONT_EXACT || o->mode == TFS_MODE_RED_BLACK, TFS_ERR_INVALID_ARG,
+         "options.mode is not a tfs_mode");
+    NEED(o->kernel >= TFS_KERNEL_AUTO && o->kernel <= TFS_KERNEL_DIAGONAL, TFS_ERR_INVALID_ARG,
+         "options.kernel is not a tfs_kernel");
+    NEED(o->temporal_block >= 0 && o->temporal_block <= tfs::kMaxTemporalBlock, TFS_ERR_INVALID_ARG,
+         "options.temporal_block out of range");
+    NEED(o->world >= 1 && o->rank >= 0 && o->rank < o->world, TFS_ERR_INVALID_ARG, "bad rank/world");
+    NEED(o->world == 1, TFS_ERR_INVALID_ARG, "multi-slab handles are not available in this build");
+    return TFS_OK;
+}
+
+// ---- phases ----------------------------------------------------------------------------------
+
+int phase_gravity(tfs_sim *s, float dt) {
+    int rc = refresh_flags(s);
+    if (rc) return rc;
+    const float gdt = s->cfg.gravity * dt;  // simulator.rs:147 (one f32 product, then one add per cell)
+    const long long n = s->n();
+    const unsigned gb = std::min<unsigned>(blocks_for(n, 256), 148 * 16);
+    tfs::k_gravity<<<gb, 256, 0, s->stream>>>(s->v, s->flags, n, gdt);
+    s->launches++;
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+int project_diagonal(tfs_sim *s, float omega, float pc) {
+    const long long W = (long long)s->W, H = (long long)s->H;
+    const int K = s->opt.iterations;
+    if (W < 3 || H < 3 || K == 0) return TFS_OK;
+    tfs::Grid g = s->grid();
+    const long long dmax = W + H - 4;
+    const long long len = std::min(W, H) - 2;
+    const int bs = 128;
+    for (long long t = 2; t <= dmax + 2LL * (K - 1); ++t) {
+        long long k_lo = std::max(0LL, (t - dmax + 1) / 2);
+        long long k_hi = std::min<long long>(K - 1, (t - 2) / 2);
+        if (k_hi < k_lo) continue;
+        dim3 grid(blocks_for(len, bs), (unsigned)(k_hi - k_lo + 1));
+        tfs::k_project_wavefront<<<grid, bs, 0, s->stream>>>(s->u, s->v, s->p, s->flags, g, t, (int)k_lo, omega, pc);
+        s->launches++;
+    }
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+int project_redblack(tfs_sim *s, float omega, float pc) {
+    tfs::Grid g = s->grid();
+    const long long half = ((long long)s->H + 1) / 2;
+    const unsigned gb = blocks_for((long long)s->W * half, 256);
+    for (int it = 0; it < s->opt.iterations; ++it)
+        for (int colour = 0; colour < 2; ++colour) {
+            tfs::k_project_redblack<<<gb, 256, 0, s->stream>>>(s->u, s->v, s->p, s->flags, g, colour, omega, pc);
+            s->launches++;
+        }
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+// make_incompressible (simulator.rs:151-190).  `fuse_gravity`: the systolic kernel can apply
+// add_gravity while it loads v, saving the separate pass.
+int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
+    int rc = refresh_flags(s);
+    if (rc) return rc;
+    if (gravity_done) *gravity_done = false;
+    const float pc = s->cfg.density / dt;  // :155 (inf for dt == 0, like the reference)
+    const float omega = s->opt.omega;
+    if (s->opt.mode == TFS_MODE_RED_BLACK) {
+        CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));  // :154
+        return project_redblack(s, omega, pc);
+    }
+    int kernel = s->opt.kernel;
+    if (kernel == TFS_KERNEL_AUTO) kernel = tfs::systolic_available() ? TFS_KERNEL_SYSTOLIC : TFS_KERNEL_DIAGONAL;
+    if (kernel == TFS_KERNEL_SYSTOLIC) {
+        NEED(tfs::systolic_available(), TFS_ERR_INVALID_ARG, "systolic kernel not built");
+        tfs::SystolicArgs a{};
+        a.u = &s->u; a.v = &s->v; a.p = &s->p; a.u2 = &s->u2; a.v2 = &s->v2; a.p2 = &s->p2;
+        a.flags = s->flags;
+        a.W = (long long)s->W; a.H = (long long)s->H;
+        a.iterations = s->opt.iterations; a.temporal_block = s->opt.temporal_block;
+        a.omega = omega; a.pc = pc;
+        a.gdt = s->cfg.gravity * dt; a.fuse_gravity = fuse_gravity;
+        a.stream = s->stream;
+        const char *msg = nullptr;
+        uint64_t launched = 0;
+        cudaError_t e = tfs::systolic_project(a, s->sys, &launched, &msg);
+        s->launches += launched;
+        if (e != cudaSuccess)
+            return fail(e == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "systolic projection: %s (%s)",
+                        cudaGetErrorString(e), msg ? msg : "");
+        if (gravity_done) *gravity_done = fuse_gravity;
+        return TFS_OK;
+    }
+    CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));  // :154
+    return project_diagonal(s, omega, pc);
+}
+
+int phase_advect(tfs_sim *s, float dt) {
+    int rc = refresh_flags(s);
+    if (rc) return rc;
+    tfs::Grid g = s->grid();
+    const long long W = (long long)s->W, H = (long long)s->H;
+    if (H % 4 == 0) {
+        tfs::k_advect<4><<<blocks_for(W * (H / 4), 256), 256, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2,
+                                                                               s->s2, g, 0, W, dt);
+    } else {
+        tfs::k_advect<1><<<blocks_for(W * H, 256), 256, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2,
+                                                                         s->s2, g, 0, W, dt);
+    }
+    s->launches++;
+    CU(cudaGetLastError());
+    std::swap(s->u, s->u2);  // simulator.rs:240-242
+    std::swap(s->v, s->v2);
+    std::swap(s->s, s->s2);
+    return TFS_OK;
+}
+
+int ensure_prof_events(tfs_sim *s) {
+    if (s->prof_created) return TFS_OK;
+    for (int i = 0; i < kMaxProfSteps; ++i)
+        for (int j = 0; j < 4; ++j) CU(cudaEventCreate(&s->prof_ev[i][j]));
+    s->prof_created = true;
+    return TFS_OK;
+}
+
+// fold recorded per-step events into the accumulators (synchronises the stream)
+int drain_prof(tfs_sim *s) {
+    if (s->prof_n == 0) return TFS_OK;
+    CU(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < s->prof_n; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, s->prof_ev[i][j], s->prof_ev[i][j + 1]));
+            s->acc_ms[j] += ms;
+        }
+    s->acc_steps += (uint64_t)s->prof_n;
+    s->prof_n = 0;
+    return TFS_OK;
+}
+
+int field_ptr(tfs_sim *s, int field, void **ptr, size_t *elem) {
+    switch (field) {
+    case TFS_FIELD_U: *ptr = s->u; *elem = 4; break;
+    case TFS_FIELD_V: *ptr = s->v; *elem = 4; break;
+    case TFS_FIELD_P: *ptr = s->p; *elem = 4; break;
+    case TFS_FIELD_S: *ptr = s->s; *elem = 4; break;
+    case TFS_FIELD_M: *ptr = s->m; *elem = 1; break;
+    case TFS_FIELD_FLAGS: *ptr = s->flags; *elem = 1; break;
+    default: return fail(TFS_ERR_INVALID_ARG, "field %d is not a tfs_field", field);
+    }
+    return TFS_OK;
+}
+
+int ensure_stage(tfs_sim *s, size_t bytes) {
+    if (s->stage_bytes >= bytes) return TFS_OK;
+    if (s->d_stage) cudaFree(s->d_stage);
+    s->d_stage = nullptr;
+    s->stage_bytes = 0;
+    CU(cudaMalloc(&s->d_stage, bytes));
+    s->stage_bytes = bytes;
+    return TFS_OK;
+}
+
+}  // namespace
+
+// ================================= C ABI =======================================================
+extern "C" {
+
+const char *tfs_version(void) { return TFS_VERSION_STRING; }
+const char *tfs_last_error(void) { return g_err; }
+
+int tfs_device_count(int *count) {
+    NEED(count, TFS_ERR_INVALID_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(TFS_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return TFS_OK;
+}
+
+void tfs_default_config(tfs_config *cfg) {
+    if (!cfg) return;
+    cfg->gravity = 0.0f;     // config.rs:19
+    cfg->wind_speed = 50.0f; // :20
+    cfg->smoke_size = 0.25f; // :21
+    cfg->density = 1000.0f;  // :22
+}
+
+void tfs_default_options(tfs_options *opt) {
+    if (!opt) return;
+    opt->iterations = 50;  // simulator.rs:153
+    opt->omega = 1.9f;     // simulator.rs:152
+    opt->mode = TFS_MODE_WAVEFRONT_EXACT;
+    opt->device = 0;
+    opt->kernel = TFS_KERNEL_AUTO;
+    opt->temporal_block = 0;
+    opt->rank = 0;
+    opt->world = 1;
+}
+
+int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_options *opt, tfs_sim **out) {
+    NEED(out, TFS_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    NEED(width >= 1 && height >= 1, TFS_ERR_INVALID_ARG,
+         "width and height must be >= 1 (the reference underflows usize at simulator.rs:367)");
+    NEED(width <= (1u << 24) && height <= (1u << 24), TFS_ERR_INVALID_ARG, "grid side exceeds 2^24 (f32 coordinates)");
+    tfs_options o;
+    tfs_default_options(&o);
+    if (opt) o = *opt;
+    int rc = check_options(&o);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(TFS_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    NEED(o.device >= 0 && o.device < ndev, TFS_ERR_INVALID_ARG, "options.device out of range");
+    tfs_sim *s = new (std::nothrow) tfs_sim();
+    NEED(s, TFS_ERR_OOM, "host allocation failed");
+    s->device = o.device;
+    s->opt = o;
+    tfs_default_config(&s->cfg);
+    if (cfg) s->cfg = *cfg;
+    s->W = width;
+    s->H = height;
+#define CREATE_TRY(x)         \
+    do {                      \
+        rc = (x);             \
+        if (rc) {             \
+            tfs_destroy(s);   \
+            return rc;        \
+        }                     \
+    } while (0)
+    CREATE_TRY(set_device(s));
+    CREATE_TRY([&]() -> int {
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s->t0));
+        CU(cudaEventCreate(&s->t1));
+        CU(cudaMalloc((void **)&s->d_part, 2 * 4096 * sizeof(float)));
+        CU(cudaMallocHost((void **)&s->h_pin, 16 * sizeof(float)));
+        return TFS_OK;
+    }());
+    CREATE_TRY(alloc_fields(s, width * height));
+    CREATE_TRY(reset_fields(s));
+    // make_block_grid (simulator.rs:113-119): the left border column is solid
+    tfs::k_fill_range_u8<<<blocks_for((long long)std::min(height, width * height), 256), 256, 0, s->stream>>>(
+        s->m, s->grid(), 0, (long long)std::min(height, width * height), 1);
+    s->launches++;
+    s->flags_dirty = true;
+    CREATE_TRY(refresh_flags(s));
+    CREATE_TRY([&]() -> int {
+        CU(cudaStreamSynchronize(s->stream));
+        return TFS_OK;
+    }());
+#undef CREATE_TRY
+    *out = s;
+    return TFS_OK;
+}
+
+int tfs_destroy(tfs_sim *s) {
+    if (!s) return TFS_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    free_fields(s);
+    tfs::systolic_release(s->sys);
+    if (s->d_part) cudaFree(s->d_part);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->d_stage) cudaFree(s->d_stage);
+    if (s->prof_created)
+        for (int i = 0; i < kMaxProfSteps; ++i)
+            for (int j = 0; j < 4; ++j) cudaEventDestroy(s->prof_ev[i][j]);
+    if (s->t0) cudaEventDestroy(s->t0);
+    if (s->t1) cudaEventDestroy(s->t1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return TFS_OK;
+}
+
+int tfs_resize(tfs_sim *s, size_t width, size_t height) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    NEED(width >= 1 && height >= 1, TFS_ERR_INVALID_ARG, "width and height must be >= 1");
+    NEED(width <= (1u << 24) && height <= (1u << 24), TFS_ERR_INVALID_ARG, "grid side exceeds 2^24");
+    int rc = set_device(s);
+    if (rc) return rc;
+    const size_t n_old = s->W * s->H, n_new = width * height, old_h = s->H;
+    // resize_block_grid (simulator.rs:121-135): clear the old left border, Vec::resize keeps the
+    // FLAT prefix (no (x,y) re-mapping), then set the first new_h entries.
+    uint8_t *m_old = s->m;
+    s->m = nullptr;  // keep across alloc_fields
+    tfs::k_fill_range_u8<<<blocks_for((long long)std::min(old_h, n_old), 256), 256, 0, s->stream>>>(
+        m_old, s->grid(), 0, (long long)std::min(old_h, n_old), 0);
+    s->launches++;
+    s->W = width;
+    s->H = height;
+    rc = alloc_fields(s, n_new);  // zero-fills m
+    if (rc) {
+        cudaFree(m_old);
+        return rc;
+    }
+    CU(cudaMemcpyAsync(s->m, m_old, std::min(n_old, n_new), cudaMemcpyDeviceToDevice, s->stream));
+    tfs::k_fill_range_u8<<<blocks_for((long long)std::min(height, n_new), 256), 256, 0, s->stream>>>(
+        s->m, s->grid(), 0, (long long)std::min(height, n_new), 1);
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    cudaFree(m_old);
+    s->flags_dirty = true;
+    rc = reset_fields(s);
+    if (rc) return rc;
+    return refresh_flags(s);
+}
+
+int tfs_restart(tfs_sim *s) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    // resize(self.width, self.height) (simulator.rs:55-57): same size, so the mask prefix copy is
+    // the identity and only the left border is rewritten; no reallocation needed.
+    int rc = set_device(s);
+    if (rc) return rc;
+    const long long hh = (long long)std::min(s->H, s->W * s->H);
+    tfs::k_fill_range_u8<<<blocks_for(hh, 256), 256, 0, s->stream>>>(s->m, s->grid(), 0, hh, 1);
+    s->launches++;
+    s->flags_dirty = true;
+    rc = reset_fields(s);
+    if (rc) return rc;
+    return refresh_flags(s);
+}
+
+int tfs_set_config(tfs_sim *s, const tfs_config *cfg) {
+    NEED(s && cfg, TFS_ERR_INVALID_ARG, "sim or cfg is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    s->cfg = *cfg;
+    return apply_wind_and_pipe(s);
+}
+
+int tfs_get_config(const tfs_sim *s, tfs_config *cfg) {
+    NEED(s && cfg, TFS_ERR_INVALID_ARG, "sim or cfg is NULL");
+    *cfg = s->cfg;
+    return TFS_OK;
+}
+
+int tfs_set_options(tfs_sim *s, const tfs_options *opt) {
+    NEED(s && opt, TFS_ERR_INVALID_ARG, "sim or opt is NULL");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    NEED(opt->device == s->device, TFS_ERR_INVALID_ARG, "the device of a handle cannot change");
+    NEED(opt->rank == s->opt.rank && opt->world == s->opt.world, TFS_ERR_INVALID_ARG, "rank/world cannot change");
+    s->opt = *opt;
+    return TFS_OK;
+}
+
+int tfs_get_options(const tfs_sim *s, tfs_options *opt) {
+    NEED(s && opt, TFS_ERR_INVALID_ARG, "sim or opt is NULL");
+    *opt = s->opt;
+    return TFS_OK;
+}
+
+int tfs_get_size(const tfs_sim *s, size_t *width, size_t *height) {
+    NEED(s && width && height, TFS_ERR_INVALID_ARG, "NULL argument");
+    *width = s->W;
+    *height = s->H;
+    return TFS_OK;
+}
+
+int tfs_set_block(tfs_sim *s, size_t x, size_t y, int value) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    const size_t idx = x * s->H + y;  // calculate_index (simulator.rs:306-308); no per-axis check, like the reference
+    if (idx >= s->W * s->H)
+        return fail(TFS_ERR_OUT_OF_RANGE, "index out of bounds: the len is %zu but the index is %zu", s->W * s->H, idx);
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(s->m + idx, value ? 1 : 0, 1, s->stream));
+    s->flags_dirty = true;
+    return TFS_OK;
+}
+
+int tfs_upload_blocks(tfs_sim *s, const uint8_t *mask, size_t offset, size_t n) {
+    NEED(s && (mask || n == 0), TFS_ERR_INVALID_ARG, "NULL argument");
+    if (offset > s->W * s->H || n > s->W * s->H - offset)
+        return fail(TFS_ERR_OUT_OF_RANGE, "range [%zu, %zu) exceeds the grid (%zu cells)", offset, offset + n, s->W * s->H);
+    if (n == 0) return TFS_OK;
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->m + offset, mask, n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));  // the caller's buffer is not retained past the call
+    s->flags_dirty = true;
+    return TFS_OK;
+}
+
+int tfs_step(tfs_sim *s, float dt) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    rc = refresh_flags(s);
+    if (rc) return rc;
+    cudaEvent_t *ev = nullptr;
+    if (s->profiling) {
+        rc = ensure_prof_events(s);
+        if (rc) return rc;
+        if (s->prof_n == kMaxProfSteps) {
+            rc = drain_prof(s);
+            if (rc) return rc;
+        }
+        ev = s->prof_ev[s->prof_n++];
+        CU(cudaEventRecord(ev[0], s->stream));
+    }
+    // gravity folds into the systolic projection's first load of v when that kernel runs
+    const bool exact = s->opt.mode == TFS_MODE_WAVEFRONT_EXACT;
+    const bool want_systolic = exact && tfs::systolic_available() &&
+                               (s->opt.kernel == TFS_KERNEL_AUTO || s->opt.kernel == TFS_KERNEL_SYSTOLIC) &&
+                               s->opt.iterations > 0;
+    if (!want_systolic) {
+        rc = phase_gravity(s, dt);
+        if (rc) return rc;
+    }
+    if (ev) CU(cudaEventRecord(ev[1], s->stream));
+    bool gravity_done = false;
+    rc = phase_project(s, dt, want_systolic, &gravity_done);
+    if (rc) return rc;
+    if (want_systolic && !gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
+    if (ev) CU(cudaEventRecord(ev[2], s->stream));
+    rc = phase_advect(s, dt);
+    if (rc) return rc;
+    if (ev) CU(cudaEventRecord(ev[3], s->stream));
+    return TFS_OK;
+}
+
+int tfs_phase_gravity(tfs_sim *s, float dt) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    return rc ? rc : phase_gravity(s, dt);
+}
+int tfs_phase_project(tfs_sim *s, float dt) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    return rc ? rc : phase_project(s, dt, false, nullptr);
+}
+int tfs_phase_advect(tfs_sim *s, float dt) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    return rc ? rc : phase_advect(s, dt);
+}
+
+int tfs_sync(tfs_sim *s) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return TFS_OK;
+}
+
+int tfs_read_view(tfs_sim *s, int field, size_t x0, size_t y0, size_t w, size_t h, void *dst) {
+    NEED(s && dst, TFS_ERR_INVALID_ARG, "NULL argument");
+    if (x0 > s->W || w > s->W - x0 || y0 > s->H || h > s->H - y0)
+        return fail(TFS_ERR_OUT_OF_RANGE, "view [%zu+%zu) x [%zu+%zu) exceeds the %zu x %zu grid", x0, w, y0, h, s->W, s->H);
+    int rc = set_device(s);
+    if (rc) return rc;
+    if (field == TFS_FIELD_FLAGS) {
+        rc = refresh_flags(s);
+        if (rc) return rc;
+    }
+    void *src = nullptr;
+    size_t elem = 0;
+    rc = field_ptr(s, field, &src, &elem);
+    if (rc) return rc;
+    if (w == 0 || h == 0) return TFS_OK;
+    if (h == s->H) {  // full-height window: columns are contiguous, no packing needed
+        CU(cudaMemcpyAsync(dst, (char *)src + x0 * s->H * elem, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        rc = ensure_stage(s, w * h * elem);
+        if (rc) return rc;
+        const long long nv = (long long)(w * h);
+        if (elem == 4)
+            tfs::k_pack_view<float><<<blocks_for(nv, 256), 256, 0, s->stream>>>((const float *)src, (float *)s->d_stage, s->grid(),
+                                                                             (long long)x0, (long long)y0, (long long)w, (long long)h);
+        else
+            tfs::k_pack_view<uint8_t><<<blocks_for(nv, 256), 256, 0, s->stream>>>((const uint8_t *)src, (uint8_t *)s->d_stage, s->grid(),
+                                                                               (long long)x0, (long long)y0, (long long)w, (long long)h);
+        s->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst, s->d_stage, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return TFS_OK;
+}
+
+int tfs_read_field(tfs_sim *s, int field, void *dst, size_t n) {
+    NEED(s && dst, TFS_ERR_INVALID_ARG, "NULL argument");
+    NEED(n == s->W * s->H, TFS_ERR_INVALID_ARG, "n must equal width*height");
+    return tfs_read_view(s, field, 0, 0, s->W, s->H, dst);
+}
+
+int tfs_write_field(tfs_sim *s, int field, const void *src, size_t n) {
+    NEED(s && src, TFS_ERR_INVALID_ARG, "NULL argument");
+    NEED(n == s->W * s->H, TFS_ERR_INVALID_ARG, "n must equal width*height");
+    NEED(field != TFS_FIELD_FLAGS, TFS_ERR_INVALID_ARG, "FLAGS is derived from M and cannot be written");
+    int rc = set_device(s);
+    if (rc) return rc;
+    void *dst = nullptr;
+    size_t elem = 0;
+    rc = field_ptr(s, field, &dst, &elem);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, src, n * elem, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (field == TFS_FIELD_M) s->flags_dirty = true;
+    return TFS_OK;
+}
+
+int tfs_pressure_minmax(tfs_sim *s, float *min_p, float *max_p) {
+    NEED(s && min_p && max_p, TFS_ERR_INVALID_ARG, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    const long long n = s->n();
+    const int nb = (int)std::min<long long>(blocks_for(n, 256 * 8), 2048);
+    tfs::k_minmax_partial<<<nb, 256, 0, s->stream>>>(s->p, n, s->d_part);
+    tfs::k_minmax_final<<<1, 256, 0, s->stream>>>(s->d_part, nb, s->d_part + 2 * 4096 - 2);
+    s->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->h_pin, s->d_part + 2 * 4096 - 2, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    *min_p = s->h_pin[0];
+    *max_p = s->h_pin[1];
+    // sim_renderer.rs:31-37 is `if x < min {..} else if x > max {..}`: an element that lowers the
+    // running minimum is not offered to the maximum.  p[0] and p[1] are always 0.0 when H >= 2
+    // (border cells are never written), after which the rule equals plain min/max; the only grid
+    // where it differs is the single-cell one, where max stays f32::MIN.
+    if (n == 1) *max_p = -3.402823466e38f;
+    return TFS_OK;
+}
+
+int tfs_divergence_linf(tfs_sim *s, float *out) {
+    NEED(s && out, TFS_ERR_INVALID_ARG, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    rc = refresh_flags(s);
+    if (rc) return rc;
+    const long long n = s->n();
+    const int nb = (int)std::min<long long>(blocks_for(n, 256 * 8), 2048);
+    tfs::k_div_partial<<<nb, 256, 0, s->stream>>>(s->u, s->v, s->flags, s->grid(), 0, (long long)s->W, s->d_part);
+    tfs::k_minmax_final<<<1, 256, 0, s->stream>>>(s->d_part, nb, s->d_part + 2 * 4096 - 2);
+    s->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->h_pin, s->d_part + 2 * 4096 - 2, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    *out = s->h_pin[1];
+    return TFS_OK;
+}
+
+int tfs_scene_disc(tfs_sim *s, long cx, long cy, long r) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    tfs::k_scene_disc<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->grid(), cx, cy, r);
+    s->launches++;
+    CU(cudaGetLastError());
+    s->flags_dirty = true;
+    return TFS_OK;
+}
+int tfs_scene_lattice(tfs_sim *s, long pitch, long r) {
+    NEED(s && pitch > 0, TFS_ERR_INVALID_ARG, "bad argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    tfs::k_scene_lattice<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->grid(), pitch, r);
+    s->launches++;
+    CU(cudaGetLastError());
+    s->flags_dirty = true;
+    return TFS_OK;
+}
+int tfs_scene_random(tfs_sim *s, uint64_t seed, uint64_t threshold) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    tfs::k_scene_random<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->grid(), seed, threshold);
+    s->launches++;
+    CU(cudaGetLastError());
+    s->flags_dirty = true;
+    return TFS_OK;
+}
+int tfs_fill_random_velocity(tfs_sim *s, uint64_t seed, float amp) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    tfs::k_fill_random_velocity<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->u, s->v, s->grid(), seed, amp);
+    s->launches++;
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+int tfs_host_alloc(void **ptr, size_t bytes) {
+    NEED(ptr, TFS_ERR_INVALID_ARG, "ptr is NULL");
+    CU(cudaMallocHost(ptr, bytes));
+    return TFS_OK;
+}
+int tfs_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return TFS_OK;
+}
+
+int tfs_timer_begin(tfs_sim *s) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaEventRecord(s->t0, s->stream));
+    return TFS_OK;
+}
+int tfs_timer_end(tfs_sim *s, float *elapsed_ms) {
+    NEED(s && elapsed_ms, TFS_ERR_INVALID_ARG, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaEventRecord(s->t1, s->stream));
+    CU(cudaEventSynchronize(s->t1));
+    CU(cudaEventElapsedTime(elapsed_ms, s->t0, s->t1));
+    return TFS_OK;
+}
+
+int tfs_set_profiling(tfs_sim *s, int enabled) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    rc = drain_prof(s);
+    if (rc) return rc;
+    s->profiling = enabled != 0;
+    s->acc_ms[0] = s->acc_ms[1] = s->acc_ms[2] = 0;
+    s->acc_steps = 0;
+    return TFS_OK;
+}
+int tfs_get_phase_ms(tfs_sim *s, float *gravity_ms, float *project_ms, float *advect_ms, uint64_t *steps) {
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    int rc = set_device(s);
+    if (rc) return rc;
+    rc = drain_prof(s);
+    if (rc) return rc;
+    if (gravity_ms) *gravity_ms = (float)s->acc_ms[0];
+    if (project_ms) *project_ms = (float)s->acc_ms[1];
+    if (advect_ms) *advect_ms = (float)s->acc_ms[2];
+    if (steps) *steps = s->acc_steps;
+    return TFS_OK;
+}
+
+int tfs_launch_count(const tfs_sim *s, uint64_t *launches) {
+    NEED(s && launches, TFS_ERR_INVALID_ARG, "NULL argument");
+    *launches = s->launches;
+    return TFS_OK;
+}
+
+int tfs_selftest_division(int device, uint64_t *mismatches) {
+    NEED(mismatches, TFS_ERR_INVALID_ARG, "mismatches is NULL");
+    CU(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc((void **)&d, sizeof(*d)));
+    CU(cudaMemset(d, 0, sizeof(*d)));
+    tfs::k_selftest_division<<<148 * 8, 256>>>(d);
+    CU(cudaGetLastError());
+    unsigned long long h = 0;
+    CU(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = h;
+    return TFS_OK;
+}
+
+int tfs_peer_export(tfs_sim *s, void *blob) {
+    NEED(s && blob, TFS_ERR_INVALID_ARG, "NULL argument");
+    return fail(TFS_ERR_COMM, "multi-slab handles are not available in this build");
+}
+int tfs_peer_attach(tfs_sim *s, const void *left_blob, const void *right_blob) {
+    (void)left_blob;
+    (void)right_blob;
+    NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    return fail(TFS_ERR_COMM, "multi-slab handles are not available in this build");
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// tfs_common.cuh -- shared device helpers for the simulator-step kernels (sm_100a).
+//
+// Bit-exactness rules: Rust evaluates every f32 operation with one rounding
+// and never contracts a*b+c.  All arithmetic that must match the reference therefore goes
+// through the __f*_rn intrinsics (which nvcc never fuses) and the library is additionally
+// compiled with -fmad=false.  FMAs appear only where the product is exact by construction
+// (a multiplier of 0.0 or 1.0), in which case fma(a,b,c) == a*b + c bit-for-bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TFS_DEVINL __device__ __forceinline__
+
+// per-cell flag byte (tfs.h TFS_FIELD_FLAGS)
+#define TFS_F_L 1u   // left neighbour is fluid   (simulator.rs:168, "left_is_block" = !block)
+#define TFS_F_R 2u   // right neighbour is fluid  (:166)
+#define TFS_F_B 4u   // bottom neighbour is fluid (:167)
+#define TFS_F_T 8u   // top neighbour is fluid    (:165)
+#define TFS_F_LIVE 16u  // !block && !border      (:161)
+
+TFS_DEVINL float fadd(float a, float b) { return __fadd_rn(a, b); }
+TFS_DEVINL float fsub(float a, float b) { return __fsub_rn(a, b); }
+TFS_DEVINL float fmul(float a, float b) { return __fmul_rn(a, b); }
+
+// index_is_border_with_size (simulator.rs:365-375) on (x, y) instead of the flat index
+TFS_DEVINL bool is_border(long long x, long long y, long long W, long long H) {
+    return x == 0 || x == W - 1 || y == 0 || y == H - 1;
+}
+
+// x / n for n in {1,2,3,4}, correctly rounded, without the slow path of a general divide.
+// rcp = RN(1/n).  q0 = RN(x*rcp); r = x - n*q0 exactly (one fma); q = RN(q0 + r*rcp).
+// For n = 1, 2, 4 rcp is exact and r == 0 in the normal range; for n = 3 this is the classic
+// Markstein correction.  tfs_selftest_division() proves equality with __fdiv_rn for all
+// 2^32 inputs x on the device; the same sequence was checked exhaustively on the host
+// (gcc -mfma, all 2^32 x, n = 1..4: 0 mismatches).
+TFS_DEVINL float div_small(float x, float nf, float rcp) {
+    float q0 = __fmul_rn(x, rcp);
+    float r = __fmaf_rn(-nf, q0, x);
+    float q = __fmaf_rn(r, rcp, q0);
+    // |x| = inf or NaN: the product already is the IEEE answer (the fma would make inf - inf).
+    // q0 == +-0 (x == +-0 or total underflow): the product is the answer and keeps the sign of
+    // x, which 0 + (-0) in the correction would lose.
+    return (fabsf(q0) <= 3.402823466e38f && q0 != 0.0f) ? q : q0;
+}
+
+// One Gauss-Seidel cell update (simulator.rs:161-186) on register operands.
+//   uC = u[idx], uR = u[right], vC = v[idx], vT = v[top], p = p[idx]; f = flag byte of the cell.
+// Operand order and rounding follow the reference exactly; s* multipliers are 0.0 / 1.0 so the
+// four face updates may use fma (exact product).  p uses mul then add (pc*corr rounds).
+TFS_DEVINL void cell_update(unsigned f, float omega, float pc, float &uC, float &uR, float &vC,
+                            float &vT, float &p) {
+    const unsigned nb = f & 15u;
+    if (!(f & TFS_F_LIVE) || nb == 0u) return;  // :161, :172
+    const int n = __popc(nb);                   // :169-170 (sum of 0/1 floats is exact)
+    const float nf = (float)n;
+    const float rcp = (n == 3) ? 0.333333343267440796f : ((n == 4) ? 0.25f : ((n == 2) ? 0.5f : 1.0f));
+    const float sL = (f & TFS_F_L) ? 1.0f : 0.0f;
+    const float sR = (f & TFS_F_R) ? 1.0f : 0.0f;
+    const float sB = (f & TFS_F_B) ? 1.0f : 0.0f;
+    const float sT = (f & TFS_F_T) ? 1.0f : 0.0f;
+    const float div = fsub(fadd(fsub(uR, uC), vT), vC);  // :176-178
+    const float corr = fmul(omega, div_small(-div, nf, rcp));  // :180
+    uC = __fmaf_rn(-corr, sL, uC);  // :181  u[idx]   -= corr * sL
+    uR = __fmaf_rn(corr, sR, uR);   // :182  u[right] += corr * sR
+    vC = __fmaf_rn(-corr, sB, vC);  // :184  v[idx]   -= corr * sB
+    vT = __fmaf_rn(corr, sT, vT);   // :185  v[top]   += corr * sT
+    p = fadd(p, fmul(pc, corr));    // :186
+}
+
+// splitmix64, shared with the oracle's scene generators (integer, bit-exact)
+__host__ TFS_DEVINL uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}

@@ -1,0 +1,405 @@
+// tfs_kernels.cuh -- streaming kernels of the simulator step: cell flags, init/edit, gravity,
+// the simple (one launch per wavefront) exact projection, red-black projection, semi-Lagrangian
+// advection and the reductions.  The temporally blocked systolic projection lives in
+// tfs_systolic.cuh.
+//
+// Layout (simulator.rs:7): idx = x*H + y, y contiguous.  Every kernel takes the GLOBAL grid
+// size (W, H); `x0` is the global x of storage column 0 and `ncols` the number of stored
+// columns (a single-GPU handle has x0 = 0, ncols = W; an x-slab stores its columns plus halos).
+#pragma once
+#include "tfs_common.cuh"
+
+namespace tfs {
+
+struct Grid {
+    long long W, H;      // global size
+    long long x0;        // global x of storage column 0
+    long long ncols;     // stored columns
+};
+
+// ---------------------------------------------------------------------------------------------
+// cell flags from the block mask (simulator.rs:161, :165-168).  Integer work, bit-exact.
+// One thread per cell of the stored range [c_begin, c_end) x [0, H).
+__global__ void k_cell_flags(const uint8_t *__restrict__ m, uint8_t *__restrict__ flags, Grid g,
+                             long long c_begin, long long c_end) {
+    const long long H = g.H;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (c_end - c_begin) * H;
+    if (t >= n) return;
+    long long lc = c_begin + t / H, y = t % H;
+    long long x = g.x0 + lc;
+    long long idx = lc * H + y;
+    unsigned f = 0;
+    if (!m[idx] && !is_border(x, y, g.W, H)) {
+        // an updatable cell is never on the border, so all four neighbours exist globally;
+        // in a slab the neighbour columns must be stored (halo >= 1), else treated as fluid=0
+        f = TFS_F_LIVE;
+        if (lc - 1 >= 0 && !m[idx - H]) f |= TFS_F_L;
+        if (lc + 1 < g.ncols && !m[idx + H]) f |= TFS_F_R;
+        if (!m[idx - 1]) f |= TFS_F_B;
+        if (!m[idx + 1]) f |= TFS_F_T;
+    }
+    flags[idx] = (uint8_t)f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// init / edit (simulator.rs:73-119, :67-71)
+__global__ void k_fill_f32(float *__restrict__ a, long long n, float x) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) a[t] = x;
+}
+__global__ void k_fill_u8(uint8_t *__restrict__ a, long long n, uint8_t x) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) a[t] = x;
+}
+// a[idx] = x for GLOBAL flat indices in [lo, hi) that fall inside the stored column range
+__global__ void k_fill_range_f32(float *__restrict__ a, Grid g, long long lo, long long hi, float x) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long gidx = lo + t;
+    if (gidx >= hi) return;
+    long long lidx = gidx - g.x0 * g.H;
+    if (lidx < 0 || lidx >= g.ncols * g.H) return;
+    a[lidx] = x;
+}
+__global__ void k_fill_range_u8(uint8_t *__restrict__ a, Grid g, long long lo, long long hi, uint8_t x) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long gidx = lo + t;
+    if (gidx >= hi) return;
+    long long lidx = gidx - g.x0 * g.H;
+    if (lidx < 0 || lidx >= g.ncols * g.H) return;
+    a[lidx] = x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// add_gravity (simulator.rs:137-149): v[idx] = v[idx] + (gravity*dt) on updatable cells.
+__global__ void k_gravity(float *__restrict__ v, const uint8_t *__restrict__ flags, long long n, float gdt) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride)
+        if (flags[t] & TFS_F_LIVE) v[t] = fadd(v[t], gdt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_incompressible, exact order, simple form: one launch per wavefront t = i + j + 2k
+// (SURVEY 8a-3).  blockIdx.y = k, threads along the anti-diagonal d = t - 2k.  Every member of
+// a wavefront touches disjoint locations, so no synchronisation is needed inside a launch.
+__global__ void k_project_wavefront(float *__restrict__ u, float *__restrict__ v, float *__restrict__ p,
+                                    const uint8_t *__restrict__ flags, Grid g, long long t, int k_lo,
+                                    float omega, float pc) {
+    const long long W = g.W, H = g.H;
+    const int k = k_lo + blockIdx.y;
+    const long long d = t - 2LL * k;
+    if (d < 2 || d > W + H - 4) return;  // interior cells have 1 <= i <= W-2, 1 <= j <= H-2
+    long long i_lo = d - (H - 2);
+    if (i_lo < 1) i_lo = 1;
+    long long i_hi = d - 1;
+    if (i_hi > W - 2) i_hi = W - 2;
+    long long i = i_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i > i_hi) return;
+    long long j = d - i;
+    long long idx = i * H + j;
+    unsigned f = flags[idx];
+    if (!(f & TFS_F_LIVE)) return;
+    float uC = u[idx], uR = u[idx + H], vC = v[idx], vT = v[idx + 1], pp = p[idx];
+    cell_update(f, omega, pc, uC, uR, vC, vT, pp);
+    u[idx] = uC;
+    u[idx + H] = uR;
+    v[idx] = vC;
+    v[idx + 1] = vT;
+    p[idx] = pp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_incompressible, red-black order (TFS_MODE_RED_BLACK): one launch per colour.  Cells of
+// one colour ((i+j)&1) touch disjoint faces.  Thread = (column i, pair index jj), j = 2*jj + par.
+__global__ void k_project_redblack(float *__restrict__ u, float *__restrict__ v, float *__restrict__ p,
+                                   const uint8_t *__restrict__ flags, Grid g, int colour, float omega,
+                                   float pc) {
+    const long long H = g.H;
+    const long long half = (H + 1) >> 1;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= g.ncols * half) return;
+    long long lc = t / half, jj = t % half;
+    long long i = g.x0 + lc;
+    long long j = 2 * jj + ((i + colour) & 1);
+    if (j >= H) return;
+    long long idx = lc * H + j;
+    unsigned f = flags[idx];
+    if (!(f & TFS_F_LIVE)) return;
+    float uC = u[idx], uR = u[idx + H], vC = v[idx], vT = v[idx + 1], pp = p[idx];
+    cell_update(f, omega, pc, uC, uR, vC, vT, pp);
+    u[idx] = uC;
+    u[idx + H] = uR;
+    v[idx] = vC;
+    v[idx + 1] = vT;
+    p[idx] = pp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// move_velocity (simulator.rs:192-298): semi-Lagrangian advection of u, v and smoke.
+// Texture-free bilinear sampling; coordinates are GLOBAL f32.
+
+enum { FT_U = 0, FT_V = 1, FT_S = 2 };
+
+// sample_vector (simulator.rs:269-298).  lx0/ncols translate global columns to storage.
+template <int FT>
+TFS_DEVINL float sample_field(const float *__restrict__ f, float x, float y, const Grid &g, float Wf,
+                              float Hf) {
+    const float dx = (FT == FT_U) ? 0.0f : 0.5f;   // :277-281
+    const float dy = (FT == FT_V) ? 0.0f : 0.5f;
+    x = fmaxf(fminf(x, Wf), 1.0f);                 // :271
+    y = fmaxf(fminf(y, Hf), 1.0f);                 // :272
+    const float xs = fsub(x, dx), ys = fsub(y, dy);
+    // xs, ys >= 0.5 here, so floor == trunc and the saturating `as usize` is a plain convert
+    long long xl = (long long)__float2uint_rz(xs);   // :283
+    if (xl > g.W - 1) xl = g.W - 1;
+    long long xr = xl + 1;                           // :284
+    if (xr > g.W - 1) xr = g.W - 1;
+    const float tx = fsub(xs, (float)xl);            // :285
+    long long yb = (long long)__float2uint_rz(ys);   // :287
+    if (yb > g.H - 1) yb = g.H - 1;
+    long long yt = yb + 1;                           // :288
+    if (yt > g.H - 1) yt = g.H - 1;
+    const float ty = fsub(ys, (float)yb);            // :289
+    const float sx = fsub(1.0f, tx), sy = fsub(1.0f, ty);  // :291-292
+    // storage columns (clamped for memory safety; halo sufficiency is checked by the host)
+    long long cl = xl - g.x0, cr = xr - g.x0;
+    cl = cl < 0 ? 0 : (cl > g.ncols - 1 ? g.ncols - 1 : cl);
+    cr = cr < 0 ? 0 : (cr > g.ncols - 1 ? g.ncols - 1 : cr);
+    const float f00 = __ldg(f + cl * g.H + yb), f10 = __ldg(f + cr * g.H + yb);
+    const float f11 = __ldg(f + cr * g.H + yt), f01 = __ldg(f + cl * g.H + yt);
+    // :294-297, left to right
+    return fadd(fadd(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11)),
+                fmul(fmul(sx, ty), f01));
+}
+
+// one cell of move_velocity; (lc, j) = storage column / row of an UPDATABLE cell
+TFS_DEVINL void advect_cell(const float *__restrict__ u, const float *__restrict__ v,
+                            const float *__restrict__ s, const Grid &g, long long lc, long long j,
+                            float dt, float Wf, float Hf, float uC, float vC, float &nu, float &nv,
+                            float &ns) {
+    const long long H = g.H;
+    const long long idx = lc * H + j;
+    const float fi = (float)(g.x0 + lc), fj = (float)j;
+    // u component (:207-213), avg_vertical (:245-255): ((((0+a)+b)+c)+d)*0.25
+    const float vL = __ldg(v + idx - H), vLT = __ldg(v + idx - H + 1), vT = __ldg(v + idx + 1);
+    const float avg_v = fmul(fadd(fadd(fadd(fadd(0.0f, vL), vLT), vT), vC), 0.25f);
+    float xp = fsub(fi, fmul(uC, dt));
+    float yp = fsub(fadd(fj, 0.5f), fmul(avg_v, dt));
+    nu = sample_field<FT_U>(u, xp, yp, g, Wf, Hf);
+    // v component (:216-224), avg_horizontal (:257-267)
+    const float uB = __ldg(u + idx - 1), uRB = __ldg(u + idx + H - 1), uR = __ldg(u + idx + H);
+    const float avg_u = fmul(fadd(fadd(fadd(fadd(0.0f, uB), uRB), uR), uC), 0.25f);
+    xp = fsub(fadd(fi, 0.5f), fmul(avg_u, dt));
+    yp = fsub(fj, fmul(vC, dt));
+    nv = sample_field<FT_V>(v, xp, yp, g, Wf, Hf);
+    // smoke (:227-237); the guard at :227 is always true for an updatable cell
+    const float cv = fmul(fadd(vC, vT), 0.5f);
+    const float cu = fmul(fadd(uC, uR), 0.5f);
+    xp = fsub(fadd(fi, 0.5f), fmul(cu, dt));
+    yp = fsub(fadd(fj, 0.5f), fmul(cv, dt));
+    ns = sample_field<FT_S>(s, xp, yp, g, Wf, Hf);
+}
+
+// VEC = 4: one thread per 4 consecutive rows of a column, 128-bit loads/stores (H % 4 == 0);
+// VEC = 1: scalar fallback for any H.  Writes EVERY cell of columns [c_begin, c_end) of the new
+// buffers (non-updatable cells copy the old value: the reference clones the Vecs, :193-195).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_advect(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
+         const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
+         float *__restrict__ ns, Grid g, long long c_begin, long long c_end, float dt) {
+    const long long H = g.H;
+    const long long per_col = H / VEC;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (c_end - c_begin) * per_col) return;
+    const long long lc = c_begin + t / per_col;
+    const long long j0 = (t % per_col) * VEC;
+    const long long idx0 = lc * H + j0;
+    const float Wf = (float)g.W, Hf = (float)g.H;
+    if (VEC == 4) {
+        const float4 u4 = *reinterpret_cast<const float4 *>(u + idx0);
+        const float4 v4 = *reinterpret_cast<const float4 *>(v + idx0);
+        const float4 s4 = *reinterpret_cast<const float4 *>(s + idx0);
+        const uchar4 f4 = *reinterpret_cast<const uchar4 *>(flags + idx0);
+        float uo[4] = {u4.x, u4.y, u4.z, u4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w};
+        float so[4] = {s4.x, s4.y, s4.z, s4.w};
+        const unsigned ff[4] = {f4.x, f4.y, f4.z, f4.w};
+        float un[4], vn[4], sn[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            un[r] = uo[r]; vn[r] = vo[r]; sn[r] = so[r];
+            if (ff[r] & TFS_F_LIVE)
+                advect_cell(u, v, s, g, lc, j0 + r, dt, Wf, Hf, uo[r], vo[r], un[r], vn[r], sn[r]);
+        }
+        *reinterpret_cast<float4 *>(nu + idx0) = make_float4(un[0], un[1], un[2], un[3]);
+        *reinterpret_cast<float4 *>(nv + idx0) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+        *reinterpret_cast<float4 *>(ns + idx0) = make_float4(sn[0], sn[1], sn[2], sn[3]);
+    } else {
+        const float uo = u[idx0], vo = v[idx0], so = s[idx0];
+        float un = uo, vn = vo, sn = so;
+        if (flags[idx0] & TFS_F_LIVE) advect_cell(u, v, s, g, lc, j0, dt, Wf, Hf, uo, vo, un, vn, sn);
+        nu[idx0] = un; nv[idx0] = vn; ns[idx0] = sn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions: warp shuffle -> one value per block -> second pass by one block.
+TFS_DEVINL float warp_min(float x) {
+    for (int o = 16; o; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+TFS_DEVINL float warp_max(float x) {
+    for (int o = 16; o; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// out[2*b] = min, out[2*b+1] = max over the block's share (NaNs are ignored, as by `<` / `>`)
+__global__ void k_minmax_partial(const float *__restrict__ a, long long n, float *__restrict__ out) {
+    __shared__ float smin[32], smax[32];
+    float mn = 3.402823466e38f, mx = -3.402823466e38f;  // f32::MAX / f32::MIN (sim_renderer.rs:24-25)
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        float x = a[t];
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { smin[w] = mn; smax[w] = mx; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        mn = l < nw ? smin[l] : 3.402823466e38f;
+        mx = l < nw ? smax[l] : -3.402823466e38f;
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (l == 0) { out[2 * blockIdx.x] = mn; out[2 * blockIdx.x + 1] = mx; }
+    }
+}
+__global__ void k_minmax_final(const float *__restrict__ part, int nblocks, float *__restrict__ out) {
+    __shared__ float smin[32], smax[32];
+    float mn = 3.402823466e38f, mx = -3.402823466e38f;
+    for (int t = threadIdx.x; t < nblocks; t += blockDim.x) {
+        mn = fminf(mn, part[2 * t]);
+        mx = fmaxf(mx, part[2 * t + 1]);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { smin[w] = mn; smax[w] = mx; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        mn = l < nw ? smin[l] : 3.402823466e38f;
+        mx = l < nw ? smax[l] : -3.402823466e38f;
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (l == 0) { out[0] = mn; out[1] = mx; }
+    }
+}
+
+// max |divergence| over updatable cells with at least one fluid neighbour (SURVEY a-12);
+// partial[b] = block max, combined by k_minmax_final's max lane (min lane unused).
+__global__ void k_div_partial(const float *__restrict__ u, const float *__restrict__ v,
+                              const uint8_t *__restrict__ flags, Grid g, long long c_begin,
+                              long long c_end, float *__restrict__ out) {
+    __shared__ float smax[32];
+    const long long H = g.H;
+    float mx = 0.0f;
+    long long t = c_begin * H + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < c_end * H; t += stride) {
+        unsigned f = flags[t];
+        if ((f & TFS_F_LIVE) && (f & 15u)) {
+            float d = fsub(fadd(fsub(u[t + H], u[t]), v[t + 1]), v[t]);
+            mx = fmaxf(mx, fabsf(d));
+        }
+    }
+    mx = warp_max(mx);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smax[w] = mx;
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        mx = l < nw ? smax[l] : 0.0f;
+        mx = warp_max(mx);
+        if (l == 0) { out[2 * blockIdx.x] = 0.0f; out[2 * blockIdx.x + 1] = mx; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// view packing: dst[(x-vx0)*vh + (y-vy0)] = src[(x-g.x0)*H + y]  (per-frame D2H staging)
+template <typename T>
+__global__ void k_pack_view(const T *__restrict__ src, T *__restrict__ dst, Grid g, long long vx0,
+                            long long vy0, long long vw, long long vh) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= vw * vh) return;
+    long long x = vx0 + t / vh, y = vy0 + t % vh;
+    dst[t] = src[(x - g.x0) * g.H + y];
+}
+
+// ---------------------------------------------------------------------------------------------
+// scenes (same integer predicates as oracle/fluid_oracle.c: orc_scene_*)
+__global__ void k_scene_disc(uint8_t *__restrict__ m, Grid g, long long cx, long long cy, long long r) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= g.ncols * g.H) return;
+    long long i = g.x0 + t / g.H, j = t % g.H;
+    long long dx = 2 * i + 1 - 2 * cx, dy = 2 * j + 1 - 2 * cy;
+    if (dx * dx + dy * dy < 4 * r * r) m[t] = 1;
+}
+__global__ void k_scene_lattice(uint8_t *__restrict__ m, Grid g, long long pitch, long long r) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= g.ncols * g.H) return;
+    long long i = g.x0 + t / g.H, j = t % g.H;
+    long long a = i / pitch, b = j / pitch;
+    if (a == 0) return;
+    long long cx = pitch / 2 + pitch * a, cy = pitch / 2 + pitch * b;
+    long long dx = 2 * i + 1 - 2 * cx, dy = 2 * j + 1 - 2 * cy;
+    if (dx * dx + dy * dy < 4 * r * r) m[t] = 1;
+}
+__global__ void k_scene_random(uint8_t *__restrict__ m, Grid g, uint64_t seed, uint64_t threshold) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= g.ncols * g.H) return;
+    long long i = g.x0 + t / g.H, j = t % g.H;
+    if (is_border(i, j, g.W, g.H)) return;
+    uint64_t gidx = (uint64_t)(i * g.H + j);
+    if (splitmix64(seed ^ gidx) < threshold) m[t] = 1;
+}
+__global__ void k_fill_random_velocity(float *__restrict__ u, float *__restrict__ v, Grid g,
+                                       uint64_t seed, float amp) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= g.ncols * g.H) return;
+    uint64_t gidx = (uint64_t)(t + g.x0 * g.H);
+    uint64_t a = splitmix64(seed ^ (2 * gidx)), b = splitmix64(seed ^ (2 * gidx + 1));
+    float fa = fmul((float)(a >> 40), 1.0f / 16777216.0f);
+    float fb = fmul((float)(b >> 40), 1.0f / 16777216.0f);
+    u[t] = fmul(fsub(fmul(fa, 2.0f), 1.0f), amp);
+    v[t] = fmul(fsub(fmul(fb, 2.0f), 1.0f), amp);
+}
+
+// exhaustive check of div_small against IEEE division: x over all 2^32 bit patterns
+__global__ void k_selftest_division(unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    const unsigned long long total = 1ull << 32;
+    unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        float x = __uint_as_float((unsigned)t);
+#pragma unroll
+        for (int n = 1; n <= 4; ++n) {
+            const float nf = (float)n;
+            const float rcp = (n == 3) ? 0.333333343267440796f : ((n == 4) ? 0.25f : ((n == 2) ? 0.5f : 1.0f));
+            float ref = __fdiv_rn(x, nf), got = div_small(x, nf, rcp);
+            bool same = (__float_as_uint(ref) == __float_as_uint(got)) || (ref != ref && got != got);
+            bad += same ? 0 : 1;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+}  // namespace tfs
