@@ -46,7 +46,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "tfs_api.cu")]
+    extra = os.environ.get("TFS_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB, os.path.join(CSRC, "tfs_api.cu")]
     env = dict(os.environ)
     # the image exports CC/CXX wrappers that are not what nvcc wants as host compiler
     host = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None

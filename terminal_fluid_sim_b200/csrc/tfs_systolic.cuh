@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "tfs_common.cuh"
@@ -59,9 +60,10 @@ struct SysParams {
     int apply_gravity;
     float omega, pc, gdt;
     float4 *bnd;    // [2][n_bands][NW][n_rec][KG] records {uRp, vCf, pout, flags word}
-    int *bnd_prog;  // [n_passes][n_bands][NW] records published
+    int *bnd_prog;  // [n_passes][n_bands] records published (all k-groups)
     int *out_prog;  // [n_passes][n_bands] rows complete
     int *ticket;
+    long long *trace;  // [NW][8] cycle sums (TFS_SYS_TRACE builds only)
 };
 
 TFS_DEVINL int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
@@ -92,53 +94,99 @@ TFS_DEVINL void cp_async_wait() {
 }
 
 // The cell update with the flags already reduced to the 4 neighbour bits (0 => no update).
-// `all_interior` is warp-uniform (a vote): the common case of 32 plain fluid cells takes a
-// straight-line path; otherwise every lane runs the general update and selects.
-TFS_DEVINL void cell_update4(unsigned nb, bool all_interior, float omega, float pc, float &uC, float &uR,
-                             float &vC, float &vT, float &p) {
-    if (all_interior) {  // n = 4, all multipliers 1.0; x/4 == x*0.25 exactly
+// Three warp-uniform variants, chosen by votes over the warp's 32 x KG cells of a step:
+//   MODE 0  every cell is a plain interior fluid cell (nb == 15): straight-line arithmetic;
+//   MODE 1  every cell is plain or not updatable (nb in {0, 15}), e.g. border rows / phantom lanes:
+//           the same arithmetic, results kept only where nb == 15;
+//   MODE 2  some cell has a solid neighbour: general update (n in 1..3, 0/1 face multipliers).
+template <int MODE>
+TFS_DEVINL void cell_update4(unsigned nb, float omega, float pc, float &uC, float &uR, float &vC, float &vT,
+                             float &p) {
+    if (MODE <= 1) {  // n = 4, all multipliers 1.0; x/4 == x*0.25 exactly (also for subnormals)
         const float div = fsub(fadd(fsub(uR, uC), vT), vC);
         const float corr = fmul(omega, fmul(-div, 0.25f));
-        uC = fsub(uC, corr);
-        uR = fadd(uR, corr);
-        vC = fsub(vC, corr);
-        vT = fadd(vT, corr);
-        p = fadd(p, fmul(pc, corr));
+        const float a = fsub(uC, corr), r = fadd(uR, corr), c = fsub(vC, corr), d = fadd(vT, corr);
+        const float pp = fadd(p, fmul(pc, corr));
+        if (MODE == 0) {
+            uC = a; uR = r; vC = c; vT = d; p = pp;
+        } else {
+            const bool on = nb != 0u;
+            uC = on ? a : uC; uR = on ? r : uR; vC = on ? c : vC; vT = on ? d : vT; p = on ? pp : p;
+        }
         return;
     }
-    float a = uC, r = uR, c = vC, d = vT, pp = p;
-    cell_update((nb ? nb : 15u) | TFS_F_LIVE, omega, pc, a, r, c, d, pp);  // branch-free; discarded if nb == 0
-    const bool on = nb != 0u;
-    uC = on ? a : uC;
-    uR = on ? r : uR;
-    vC = on ? c : vC;
-    vT = on ? d : vT;
-    p = on ? pp : p;
+    // general: branch-free decode of n, 1/n and the 0/1 face multipliers (simulator.rs:165-170)
+    const int n = __popc(nb);
+    const float nf = (float)n;
+    // RN(1/n): exact power of two for n = 1, 2, 4 (exponent arithmetic), 0x3eaaaaab for n = 3
+    const float rcp_p2 = __int_as_float(0x3f800000 - ((n >> 1) << 23));
+    const float rcp = (n == 3) ? 0.333333343267440796f : rcp_p2;
+    const float sL = (nb & TFS_F_L) ? 1.0f : 0.0f;
+    const float sR = (nb & TFS_F_R) ? 1.0f : 0.0f;
+    const float sB = (nb & TFS_F_B) ? 1.0f : 0.0f;
+    const float sT = (nb & TFS_F_T) ? 1.0f : 0.0f;
+    const float div = fsub(fadd(fsub(uR, uC), vT), vC);        // :176-178
+    const float corr = fmul(omega, div_small(-div, nf, rcp));  // :180 (n == 0: garbage, discarded below)
+    const float a = __fmaf_rn(-corr, sL, uC);                  // :181  exact products, see tfs_common.cuh
+    const float r = __fmaf_rn(corr, sR, uR);                   // :182
+    const float c = __fmaf_rn(-corr, sB, vC);                  // :184
+    const float d = __fmaf_rn(corr, sT, vT);                   // :185
+    const float pp = fadd(p, fmul(pc, corr));                  // :186
+    const bool on = nb != 0u;                                  // :161, :172
+    uC = on ? a : uC; uR = on ? r : uR; vC = on ? c : vC; vT = on ? d : vT; p = on ? pp : p;
 }
 
+// optional per-segment cycle accounting of the compute warps (-DTFS_SYS_TRACE; debugging aid only)
+#ifdef TFS_SYS_TRACE
+#define TFS_TR_DECL long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64();
+#define TFS_TR(i) { long long now_ = clock64(); tr_acc[i] += now_ - tr_t; tr_t = now_; }
+#else
+#define TFS_TR_DECL
+#define TFS_TR(i)
+#endif
+
+// named barriers (id 0 is __syncthreads)
+// (ids are immediates so that ptxas reserves only the barriers actually used)
+template <int ID, int COUNT>
+TFS_DEVINL void bar_sync_imm() { asm volatile("bar.sync %0, %1;\n" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+TFS_DEVINL void bar_arrive_imm() { asm volatile("bar.arrive %0, %1;\n" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID0, int COUNT>
+TFS_DEVINL void bar_sync2(int parity) {  // double-buffered barrier pair ID0 / ID0+1
+    if (parity & 1) bar_sync_imm<ID0 + 1, COUNT>(); else bar_sync_imm<ID0, COUNT>();
+}
+template <int ID0, int COUNT>
+TFS_DEVINL void bar_arrive2(int parity) {
+    if (parity & 1) bar_arrive_imm<ID0 + 1, COUNT>(); else bar_arrive_imm<ID0, COUNT>();
+}
+enum { BAR_STEP = 1, BAR_READY0 = 2, BAR_FREE0 = 4 };  // READY/FREE are double-buffered: +0 / +1
+
+// Warp roles: warps 0..NW-1 are the k-groups (compute); warp NW is the IO warp, which owns every
+// global-memory wait: it polls the progress counters, stages the k = 0 operands and the left
+// band's records one chunk (S steps) ahead with cp.async, flushes the finished chunk's final
+// values and publishes progress behind ONE gpu-scope fence per chunk.  Compute warps never spin
+// and never fence; they meet the IO warp only at chunk boundaries through named barriers.
 template <int KG, int NW, int S, int D>
-__global__ void __launch_bounds__(32 * NW) k_project_systolic(SysParams P) {
+__global__ void __launch_bounds__(32 * (NW + 1)) k_project_systolic(SysParams P) {
     constexpr int KB = KG * NW;
     constexpr int PITCH = S + 1;               // words per lane row of a staged f32 tile
     constexpr int FW = ((S + 4 + 3) / 4) | 1;  // words per lane row of the staged flag bytes
-    constexpr int G = 4;                       // records per progress publication
-    constexpr int NT = 32 * NW;
-    static_assert(S > D + 1, "staging groups must be older than the record ring depth");
+    constexpr int NCT = 32 * NW;               // compute threads
+    constexpr int NALL = 32 * (NW + 1);
     static_assert(KG >= 1 && KG <= 8, "a k-group's flags are packed 4 bits per iteration into 32 bits");
+    static_assert((S * KG) % 2 == 0, "record chunks are copied 16 B per lane");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *s_in = reinterpret_cast<float *>(smem_raw);                      // [2][3][32][PITCH]
+    float *s_in = reinterpret_cast<float *>(smem_raw);                         // [2][3][32][PITCH]
     unsigned *s_fl = reinterpret_cast<unsigned *>(s_in + 2 * 3 * 32 * PITCH);  // [2][32][FW]
-    float *s_out = reinterpret_cast<float *>(s_fl + 2 * 32 * FW);           // [3][32][PITCH]
-    float4 *s_grp = reinterpret_cast<float4 *>(s_out + 3 * 32 * PITCH);   // [2][NW][32] (all sizes above are multiples of 16 B)
-    float4 *s_ring = s_grp + 2 * NW * 32;                                   // [NW][D+1][KG]
-    float4 *s_zero = s_ring + NW * (D + 1) * KG;                            // [KG] zeros
+    float *s_out = reinterpret_cast<float *>(s_fl + 2 * 32 * FW);              // [2][3][32][PITCH]
+    float4 *s_grp = reinterpret_cast<float4 *>(s_out + 2 * 3 * 32 * PITCH);    // [2][NW][32]
+    float4 *s_ring = s_grp + 2 * NW * 32;                                      // [2][NW][S][KG]
     __shared__ int s_task;
 
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const bool io_warp = g == NW;
     const long long W = P.W, H = P.H;
-    float4 *my_ring = s_ring + g * (D + 1) * KG;
-    if (threadIdx.x < KG) s_zero[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (;;) {
         __syncthreads();  // previous task fully retired (smem reuse, s_task)
@@ -148,252 +196,332 @@ __global__ void __launch_bounds__(32 * NW) k_project_systolic(SysParams P) {
         if (task >= P.n_passes * P.n_bands) break;
         const int tb = task / P.n_bands, b = task % P.n_bands;
         const int k_act = (tb == P.n_passes - 1) ? P.k_last : KB;
-        const float *__restrict__ gin_u = P.buf[tb & 1][0];
-        const float *__restrict__ gin_v = P.buf[tb & 1][1];
-        const float *__restrict__ gin_p = P.buf[tb & 1][2];
-        float *__restrict__ gout_u = P.buf[(tb + 1) & 1][0];
-        float *__restrict__ gout_v = P.buf[(tb + 1) & 1][1];
-        float *__restrict__ gout_p = P.buf[(tb + 1) & 1][2];
         const bool first_pass = tb == 0;
-        const bool grav = first_pass && P.apply_gravity;
-        const long long q = (long long)b * 32 + lane - 1;  // skewed coordinate of this lane
-        const long long q0 = (long long)b * 32 - 1;        // ... of lane 0
-        // record streams of this k-group
+        const long long q0 = (long long)b * 32 - 1;  // skewed coordinate of lane 0
         const bool has_left = b > 0;
-        const size_t rec_stride = (size_t)P.n_rec * KG;
-        const float4 *rec_in = P.bnd + (((size_t)(tb & 1) * P.n_bands + (b - 1)) * NW + g) * rec_stride;
-        float4 *rec_out = P.bnd + (((size_t)(tb & 1) * P.n_bands + b) * NW + g) * rec_stride;
-        const int *left_prog = P.bnd_prog + ((size_t)tb * P.n_bands + (b - 1)) * NW + g;
-        int *my_prog = P.bnd_prog + ((size_t)tb * P.n_bands + b) * NW + g;
-        int *my_out_prog = P.out_prog + (size_t)tb * P.n_bands + b;
-        const int *dep_out0 = P.out_prog + (size_t)(tb - 1) * P.n_bands + b;
-        const int *dep_out1 = P.out_prog + (size_t)(tb - 1) * P.n_bands + min(b + 1, P.n_bands - 1);
-        int known_left = 0, known_rows = first_pass ? (int)H : 0;
+        const size_t rec_stride = (size_t)P.n_rec * KG;  // float4 per (band, k-group)
+        const int n_chunks = (P.T + S - 1) / S;
 
-        // rows [0, need) of the previous pass must be final in bands b and b+1 (CTA-uniform call)
-        auto wait_rows = [&](int need) {
-            if (need > (int)H) need = (int)H;
-            if (known_rows >= need) return;
-            int k0 = 0;
-            do {
-                if (lane == 0) k0 = min(ld_volatile(dep_out0), ld_volatile(dep_out1));
-                k0 = __shfl_sync(0xffffffffu, k0, 0);
-            } while (k0 < need);
-            known_rows = k0;
-            fence_gpu();  // acquire: the (L1-allocating) stage loads below see the producers' stores
-        };
-        // chunk c holds the k = 0 operands of steps tau in [c*S, (c+1)*S): for lane l
-        //   U[l][s] = u[q_l + 1, tau - l - 1],  V[l][s] = v[q_l, tau - l],  P[l][s] = p[q_l, tau - l - 1],
-        //   flag bytes of rows tau - l - 1 .. (+S).  All NT threads share the copy work.
-        auto issue_chunk = [&](int c) {
-            const int bufi = c & 1;
-            float *su = s_in + (bufi * 3 + 0) * 32 * PITCH;
-            float *sv = s_in + (bufi * 3 + 1) * 32 * PITCH;
-            float *sp = s_in + (bufi * 3 + 2) * 32 * PITCH;
-            unsigned *sf = s_fl + bufi * 32 * FW;
-            const long long nmax = P.ncells - 1;
-            for (int e = threadIdx.x; e < 32 * S; e += NT) {
-                const int cc = e / S, r = e % S;
-                const long long col = q0 + cc;
-                const long long row = (long long)c * S + r - cc - 1;  // tau - l - 1
-                long long iu = (col + 1) * H + row, iv = col * H + row + 1, ip = col * H + row;
-                iu = iu < 0 ? 0 : (iu > nmax ? nmax : iu);  // out-of-range operands are masked at use
-                iv = iv < 0 ? 0 : (iv > nmax ? nmax : iv);
-                ip = ip < 0 ? 0 : (ip > nmax ? nmax : ip);
-                cp_async4(su + cc * PITCH + r, gin_u + iu);
-                cp_async4(sv + cc * PITCH + r, gin_v + iv);
-                if (!first_pass) cp_async4(sp + cc * PITCH + r, gin_p + ip);
-            }
-            // flag bytes: aligned words covering rows [row0, row0 + S] of each column
-            for (int e = threadIdx.x; e < 32 * FW; e += NT) {
-                const int cc = e / FW, wd = e % FW;
-                const long long col = q0 + cc;
-                const long long row0 = (long long)c * S - cc - 1;
-                long long a = ((col * H + row0) >> 2) + wd;   // arithmetic shift: floor for negatives
-                const long long amax = (P.ncells + 56) >> 2;  // the arrays carry 64 bytes of padding
-                a = a < 0 ? 0 : (a > amax ? amax : a);
-                cp_async4(sf + cc * FW + wd, reinterpret_cast<const unsigned *>(P.flags) + a);
-            }
-            cp_async_commit();
-        };
-        // final values of steps [t_first, t_last] (one chunk's worth of slots): lane l, step t <->
-        // cell column q_l - (KB-1), row t - l - KB.  All NT threads share the stores.
-        auto flush_out = [&](int t_first, int t_last) {
-            for (int e = threadIdx.x; e < 32 * S; e += NT) {
-                const int cc = e / S, s = e % S;
-                const int t = t_first + s;
-                if (t > t_last) continue;
-                const long long col = q0 + cc - (KB - 1);
-                const long long row = (long long)t - cc - KB;
-                if (col >= 0 && col < W && row >= 0 && row < H) {
-                    const long long idx = col * H + row;
-                    gout_u[idx] = s_out[(0 * 32 + cc) * PITCH + s];
-                    gout_v[idx] = s_out[(1 * 32 + cc) * PITCH + s];
-                    gout_p[idx] = s_out[(2 * 32 + cc) * PITCH + s];
+        if (io_warp) {
+            // ================================ IO warp ================================================
+            const float *__restrict__ gin_u = P.buf[tb & 1][0];
+            const float *__restrict__ gin_v = P.buf[tb & 1][1];
+            const float *__restrict__ gin_p = P.buf[tb & 1][2];
+            float *__restrict__ gout_u = P.buf[(tb + 1) & 1][0];
+            float *__restrict__ gout_v = P.buf[(tb + 1) & 1][1];
+            float *__restrict__ gout_p = P.buf[(tb + 1) & 1][2];
+            const float4 *rec_in = P.bnd + ((size_t)(tb & 1) * P.n_bands + (b - 1)) * NW * rec_stride;
+            const int *left_prog = P.bnd_prog + (size_t)tb * P.n_bands + (b - 1);
+            int *my_prog = P.bnd_prog + (size_t)tb * P.n_bands + b;
+            int *my_out_prog = P.out_prog + (size_t)tb * P.n_bands + b;
+            const int *dep_out0 = P.out_prog + (size_t)(tb - 1) * P.n_bands + b;
+            const int *dep_out1 = P.out_prog + (size_t)(tb - 1) * P.n_bands + min(b + 1, P.n_bands - 1);
+            int known_left = 0, known_rows = first_pass ? (int)H : 0;
+
+            // spin until rows [0, need_rows) of the previous pass are final in bands b, b+1 and the
+            // left band has published records [0, need_rec); returns after the counters were seen.
+            auto wait_deps = [&](int need_rows, int need_rec) {
+                if (need_rows > (int)H) need_rows = (int)H;
+                if (need_rec > P.n_rec) need_rec = P.n_rec;
+                while (known_rows < need_rows) {
+                    int k0 = 0;
+                    if (lane == 0) k0 = min(ld_volatile(dep_out0), ld_volatile(dep_out1));
+                    known_rows = __shfl_sync(0xffffffffu, k0, 0);
                 }
-            }
-        };
-
-        // ---- pipeline registers of this k-group ------------------------------------------------------
-        float uL[KG], uRo[KG], vB[KG], vTo[KG], pin[KG], pd[KG];
-#pragma unroll
-        for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
-        unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
-
-        // k = 0 operands of step tau from the staged chunk tau / S (k-group 0 only)
-        auto prep_k0 = [&](int tau) {
-            const int c = tau / S, s = tau % S, bufi = c & 1;
-            const long long row = (long long)tau - lane - 1;
-            const bool col_ok = q >= 0 && q < W;
-            const bool row_ok = row >= 0 && row < H;
-            const bool rowp_ok = row + 1 >= 0 && row + 1 < H;
-            const float su = s_in[((bufi * 3 + 0) * 32 + lane) * PITCH + s];
-            const float sv = s_in[((bufi * 3 + 1) * 32 + lane) * PITCH + s];
-            const float sp = s_in[((bufi * 3 + 2) * 32 + lane) * PITCH + s];
-            const long long row0 = (long long)c * S - lane - 1;
-            const int off = (int)((q * H + row0) & 3) + s;  // byte offset inside the staged aligned words
-            const unsigned char *fb = reinterpret_cast<const unsigned char *>(s_fl + (bufi * 32 + lane) * FW);
-            const unsigned f0 = (col_ok && row_ok) ? fb[off] : 0u;
-            const unsigned f1 = (col_ok && rowp_ok) ? fb[off + 1] : 0u;
-            uRo[0] = (q + 1 >= 0 && q + 1 < W && row_ok) ? su : 0.0f;
-            float vv = (col_ok && rowp_ok) ? sv : 0.0f;
-            if (grav && (f1 & TFS_F_LIVE)) vv = fadd(vv, P.gdt);  // simulator.rs:147
-            vTo[0] = vv;
-            pin[0] = (!first_pass && col_ok && row_ok) ? sp : 0.0f;
-            fl = (fl & ~0xFu) | (f0 & 15u);
-        };
-        auto poll_left = [&](int r) {
-            if (known_left > r) return;
-            int k0 = 0;
-            do {
-                if (lane == 0) k0 = ld_volatile(left_prog);
-                k0 = __shfl_sync(0xffffffffu, k0, 0);
-            } while (k0 <= r);
-            known_left = k0;
-            fence_gpu();
-        };
-
-        // ---- prologue ---------------------------------------------------------------------------------
-        wait_rows(S + 1);
-        issue_chunk(0);
-        wait_rows(2 * S + 1);
-        issue_chunk(1);
-        cp_async_wait<1>();  // chunk 0 landed (this thread's part)
-        if (has_left) {
-            for (int r = 0; r < D; ++r) {  // record r is consumed at the end of step r
-                if (r < P.n_rec) {
-                    poll_left(r);
-                    if (lane < KG) cp_async16_cg(my_ring + (r % (D + 1)) * KG + lane, rec_in + (size_t)r * KG + lane);
+                while (has_left && known_left < need_rec) {
+                    int k0 = 0;
+                    if (lane == 0) k0 = ld_volatile(left_prog);
+                    known_left = __shfl_sync(0xffffffffu, k0, 0);
                 }
-                cp_async_commit();
-            }
-        }
-        __syncthreads();  // chunk 0 visible to k-group 0
-        if (g == 0) prep_k0(0);
-
-        // ---- main loop ----------------------------------------------------------------------------------
-        for (int t = 0; t < P.T; ++t) {
-            if (has_left) {
-                const int r = t + D;
-                if (r < P.n_rec) {
-                    poll_left(r);
-                    if (lane < KG) cp_async16_cg(my_ring + (r % (D + 1)) * KG + lane, rec_in + (size_t)r * KG + lane);
+            };
+            // chunk c holds the k = 0 operands of steps tau in [c*S, (c+1)*S): for lane l
+            //   U[l][s] = u[q_l + 1, tau - l - 1],  V[l][s] = v[q_l, tau - l],  P[l][s] = p[q_l, tau - l - 1],
+            //   flag bytes of rows tau - l - 1 .. (+S); plus the left band's records of those steps.
+            auto issue_chunk = [&](int c) {
+                const int bufi = c & 1;
+                float *su = s_in + (bufi * 3 + 0) * 32 * PITCH;
+                float *sv = s_in + (bufi * 3 + 1) * 32 * PITCH;
+                float *sp = s_in + (bufi * 3 + 2) * 32 * PITCH;
+                unsigned *sf = s_fl + bufi * 32 * FW;
+                const long long nmax = P.ncells - 1;
+#pragma unroll 4
+                for (int e = lane; e < 32 * S; e += 32) {
+                    const int cc = e / S, r = e % S;
+                    const long long col = q0 + cc;
+                    const long long row = (long long)c * S + r - cc - 1;  // tau - l - 1
+                    long long iu = (col + 1) * H + row, iv = col * H + row + 1, ip = col * H + row;
+                    iu = iu < 0 ? 0 : (iu > nmax ? nmax : iu);  // out-of-range operands are masked at use
+                    iv = iv < 0 ? 0 : (iv > nmax ? nmax : iv);
+                    ip = ip < 0 ? 0 : (ip > nmax ? nmax : ip);
+                    cp_async4(su + cc * PITCH + r, gin_u + iu);
+                    cp_async4(sv + cc * PITCH + r, gin_v + iv);
+                    if (!first_pass) cp_async4(sp + cc * PITCH + r, gin_p + ip);
                 }
-                cp_async_commit();
-                cp_async_wait<D>();  // record t has landed in the ring
-                __syncwarp();
-            }
-            const float4 *lrec = (has_left && t < P.n_rec) ? (my_ring + (t % (D + 1)) * KG) : s_zero;
-            const int r_out = t - 32;  // the next band consumes this step's record at the end of ITS step r_out
-            const bool g_out = (lane == 31) && r_out >= 0 && r_out < P.n_rec;
-            float4 *rec_dst = rec_out + (size_t)(r_out < 0 ? 0 : r_out) * KG;
-            const unsigned fl_used = fl;
-            float4 grp_out = make_float4(0.f, 0.f, 0.f, 0.f);
-            // KG cell updates, kk descending so that every next-step operand is written in place
-#pragma unroll
-            for (int kk = KG - 1; kk >= 0; --kk) {
-                const int k = g * KG + kk;
-                unsigned nb = (fl_used >> (4 * kk)) & 15u;
-                if (k >= k_act) nb = 0u;
-                const bool all_interior = __all_sync(0xffffffffu, nb == 15u);
-                float a = uL[kk], r = uRo[kk], c = vB[kk], d = vTo[kk], pp = pin[kk];
-                cell_update4(nb, all_interior, P.omega, P.pc, a, r, c, d, pp);
-                // a = uCf (u of the cell after iteration k), r = uRp, c = vCf, d = vTp, pp = pout
-                st_global_v4_if(g_out, rec_dst + kk, make_float4(r, c, pp, kk == 0 ? __uint_as_float(fl_used) : 0.0f));
-                const float4 lr = lrec[kk];  // what "lane -1" (lane 31 of the left band) produced; broadcast read
-                float n_uL = __shfl_up_sync(0xffffffffu, r, 1);
-                float s_v = __shfl_up_sync(0xffffffffu, c, 1);
-                float s_p = __shfl_up_sync(0xffffffffu, pp, 1);
-                if (lane == 0) { n_uL = lr.x; s_v = lr.y; s_p = lr.z; }
-                vB[kk] = d;
-                uL[kk] = n_uL;
-                if (kk + 1 < KG) {
-                    uRo[kk + 1] = a;
-                    vTo[kk + 1] = s_v;
-                    pin[kk + 1] = pd[kk + 1];  // filled at the end of step t-1 (two-step path)
-                    pd[kk + 1] = s_p;
-                } else {
-                    grp_out.x = a; grp_out.y = s_v; grp_out.z = s_p;
-                    if (g == NW - 1) {  // iteration KB-1 retired: final values of the pass -> output stage
-                        const int slot = t % S;
-                        s_out[(0 * 32 + lane) * PITCH + slot] = a;
-                        s_out[(1 * 32 + lane) * PITCH + slot] = c;
-                        s_out[(2 * 32 + lane) * PITCH + slot] = pp;
+                // flag bytes: aligned words covering rows [row0, row0 + S] of each column
+                for (int e = lane; e < 32 * FW; e += 32) {
+                    const int cc = e / FW, wd = e % FW;
+                    const long long col = q0 + cc;
+                    const long long row0 = (long long)c * S - cc - 1;
+                    long long a = ((col * H + row0) >> 2) + wd;   // arithmetic shift: floor for negatives
+                    const long long amax = (P.ncells + 56) >> 2;  // the arrays carry 64 bytes of padding
+                    a = a < 0 ? 0 : (a > amax ? amax : a);
+                    cp_async4(sf + cc * FW + wd, reinterpret_cast<const unsigned *>(P.flags) + a);
+                }
+                // records [c*S, (c+1)*S) of every k-group (record r is consumed at the end of step r)
+                if (has_left) {
+                    float4 *dst = s_ring + (size_t)bufi * NW * S * KG;
+                    for (int e = lane; e < NW * S * KG; e += 32) {
+                        const int gg = e / (S * KG), x = e % (S * KG);
+                        long long r4 = (long long)c * S * KG + x;  // float4 index inside the group's stream
+                        if (r4 >= (long long)rec_stride) r4 = (long long)rec_stride - 1;  // past the end: masked at use
+                        cp_async16_cg(dst + e, rec_in + (size_t)gg * rec_stride + r4);
                     }
                 }
-            }
-            {
-                // flags: two-step path (used at t by lane L-1, needed at t+2 by lane L one slot higher)
-                unsigned s_flv = __shfl_up_sync(0xffffffffu, fl_used, 1);
-                if (lane == 0) s_flv = __float_as_uint(lrec[0].w);
-                grp_out.w = __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u);
-                fl = fld;            // filled at the end of step t-1; slot 0 is set below / by prep_k0
-                fld = s_flv << 4;
-            }
-            // hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, lane L-1's flags}
-            s_grp[((t & 1) * NW + g) * 32 + lane] = grp_out;
-            if (g_out && (((r_out + 1) % G) == 0 || r_out + 1 == P.n_rec)) {
-                fence_gpu();
-                st_volatile(my_prog, r_out + 1);
-            }
-            __syncthreads();
-            if (g > 0) {
-                const float4 gi = s_grp[((t & 1) * NW + (g - 1)) * 32 + lane];
-                uRo[0] = gi.x;
-                vTo[0] = gi.y;
-                pin[0] = pd[0];
-                pd[0] = gi.z;
-                fld |= __float_as_uint(gi.w);  // the nibble for slot 0, two steps from now
-            }
-            // ---- chunk boundary ---------------------------------------------------------------------------
-            if ((t + 1) % S == 0) {
-                const int c_next = (t + 1) / S;  // chunk that serves steps t+1 .. t+S
-                flush_out(t + 1 - S, t);
-                if (!has_left) cp_async_wait<0>();  // chunk c_next landed (with a ring: older than the ring depth)
-                fence_gpu();                         // release the flushed rows
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    // rows complete for every lane of the band: lane 31 has just retired row t - 32 - KB + 1
+                cp_async_commit();
+            };
+            // final values of chunk c (steps [c*S, (c+1)*S) and < T): lane l, step t <-> cell
+            //   column q_l - (KB-1), row t - l - KB
+            auto flush_chunk = [&](int c) {
+                const float *so = s_out + (size_t)(c & 1) * 3 * 32 * PITCH;
+#pragma unroll 4
+                for (int e = lane; e < 32 * S; e += 32) {
+                    const int cc = e / S, s = e % S;
+                    const int t = c * S + s;
+                    const long long col = q0 + cc - (KB - 1);
+                    const long long row = (long long)t - cc - KB;
+                    if (t < P.T && col >= 0 && col < W && row >= 0 && row < H) {
+                        const long long idx = col * H + row;
+                        gout_u[idx] = so[(0 * 32 + cc) * PITCH + s];
+                        gout_v[idx] = so[(1 * 32 + cc) * PITCH + s];
+                        gout_p[idx] = so[(2 * 32 + cc) * PITCH + s];
+                    }
+                }
+            };
+            auto publish = [&](int c_done) {
+                // after chunk c_done: lane 31 has retired row t - 32 - KB + 1 with t = (c_done+1)*S - 1,
+                // and records up to step t (record index t - 32) are written
+                const int t = min((c_done + 1) * S, P.T) - 1;
+                if (lane == 0) {
                     int rows = t - 32 - KB + 2;
-                    if (rows > 0) st_volatile(my_out_prog, rows > (int)H ? (int)H : rows);
+                    rows = rows < 0 ? 0 : (rows > (int)H ? (int)H : rows);
+                    int recs = t - 32 + 1;
+                    recs = recs < 0 ? 0 : (recs > P.n_rec ? P.n_rec : recs);
+                    if (c_done == n_chunks - 1) { rows = (int)H; recs = P.n_rec; }
+                    st_volatile(my_out_prog, rows);
+                    st_volatile(my_prog, recs);
                 }
-                if ((long long)(c_next + 1) * S < (long long)P.T) {
-                    wait_rows((c_next + 2) * S + 1);
-                    issue_chunk(c_next + 1);
-                } else {
-                    cp_async_commit();
+            };
+
+            TFS_TR_DECL
+            wait_deps(S + 1, S);
+            fence_gpu();
+            issue_chunk(0);
+            cp_async_wait<0>();
+            bar_arrive2<BAR_READY0, NALL>(0);
+            TFS_TR(0)
+            for (int c = 0; c < n_chunks; ++c) {
+                if (c >= 1) {
+                    bar_sync2<BAR_FREE0, NALL>(c - 1);  // compute finished chunk c-1
+                    __syncwarp();
+                    TFS_TR(1)
+                    flush_chunk(c - 1);
+                    TFS_TR(2)
+                    fence_gpu();  // release the flushed rows and the records the compute warps wrote
+                    publish(c - 1);  // promptly: dependants must never wait on OUR dependencies
+                    TFS_TR(3)
+                }
+                if (c + 1 < n_chunks) {
+                    wait_deps((c + 2) * S + 1, (c + 2) * S);
+                    TFS_TR(4)
+                    fence_gpu();  // acquire what the counters announced
+                    TFS_TR(5)
+                    issue_chunk(c + 1);
+                    TFS_TR(6)
+                    cp_async_wait<0>();
+                    bar_arrive2<BAR_READY0, NALL>(c + 1);
+                    TFS_TR(7)
                 }
             }
-            if (g == 0 && t + 1 < P.T) prep_k0(t + 1);
+            bar_sync2<BAR_FREE0, NALL>(n_chunks - 1);
+            flush_chunk(n_chunks - 1);
+            fence_gpu();
+            publish(n_chunks - 1);
+#ifdef TFS_SYS_TRACE
+            if (lane == 0 && P.trace) {
+                for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[(NW * 8 + i)], (unsigned long long)tr_acc[i]);
+            }
+#endif
+        } else {
+            // ================================ compute warps ========================================
+            const bool grav = first_pass && P.apply_gravity;
+            const long long q = q0 + lane;
+            float4 *rec_out = P.bnd + (((size_t)(tb & 1) * P.n_bands + b) * NW + g) * rec_stride;
+
+            float uL[KG], uRo[KG], vB[KG], vTo[KG], pin[KG], pd[KG];
+#pragma unroll
+            for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
+            unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
+
+            // staged k = 0 operands of step tau, loaded early (software pipelining) into plain values
+            struct K0 { float su, sv, sp; unsigned f0, f1; };
+            auto load_k0 = [&](int tau) -> K0 {
+                const int c = tau / S, s = tau % S, bufi = c & 1;
+                K0 o;
+                o.su = s_in[((bufi * 3 + 0) * 32 + lane) * PITCH + s];
+                o.sv = s_in[((bufi * 3 + 1) * 32 + lane) * PITCH + s];
+                o.sp = s_in[((bufi * 3 + 2) * 32 + lane) * PITCH + s];
+                const long long row0 = (long long)c * S - lane - 1;
+                const int off = (int)((q * H + row0) & 3) + s;  // byte offset inside the staged aligned words
+                const unsigned char *fb = reinterpret_cast<const unsigned char *>(s_fl + (bufi * 32 + lane) * FW);
+                o.f0 = fb[off];
+                o.f1 = fb[off + 1];
+                return o;
+            };
+            auto apply_k0 = [&](int tau, const K0 &o) {
+                const long long row = (long long)tau - lane - 1;
+                const bool col_ok = q >= 0 && q < W;
+                const bool row_ok = row >= 0 && row < H;
+                const bool rowp_ok = row + 1 >= 0 && row + 1 < H;
+                const unsigned f0 = (col_ok && row_ok) ? o.f0 : 0u;
+                const unsigned f1 = (col_ok && rowp_ok) ? o.f1 : 0u;
+                uRo[0] = (q + 1 >= 0 && q + 1 < W && row_ok) ? o.su : 0.0f;
+                float vv = (col_ok && rowp_ok) ? o.sv : 0.0f;
+                if (grav && (f1 & TFS_F_LIVE)) vv = fadd(vv, P.gdt);  // simulator.rs:147
+                vTo[0] = vv;
+                pin[0] = (!first_pass && col_ok && row_ok) ? o.sp : 0.0f;
+                fl = (fl & ~0xFu) | (f0 & 15u);
+            };
+            constexpr unsigned FULL = (KG == 8) ? 0xFFFFFFFFu : ((1u << (4 * KG)) - 1u);
+            const bool group_active = (g + 1) * KG <= k_act;  // every iteration of this k-group runs in this pass
+
+            TFS_TR_DECL
+            for (int c = 0; c < n_chunks; ++c) {
+                TFS_TR(0)
+                bar_sync2<BAR_READY0, NALL>(c);  // stage + records of chunk c have landed
+                TFS_TR(6)
+                if (g == 0) apply_k0(c * S, load_k0(c * S));
+                const float4 *ring = s_ring + ((size_t)(c & 1) * NW + g) * S * KG;
+                float *so = s_out + (size_t)(c & 1) * 3 * 32 * PITCH;
+                const int s_end = min(S, P.T - c * S);
+                for (int s = 0; s < s_end; ++s) {
+                    const int t = c * S + s;
+                    TFS_TR(0)
+                    const bool use_left = has_left && t < P.n_rec;
+                    // ---- early loads: left band's record (for lane 0) and next step's k = 0 operands
+                    float4 lr[KG];
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk) {
+                        lr[kk] = ring[s * KG + kk];  // broadcast read; only lane 0 uses it (and only if use_left)
+                    }
+                    const bool have_next = (g == 0) && (s + 1 < s_end);
+                    K0 nk0 = {0.f, 0.f, 0.f, 0u, 0u};
+                    if (have_next) nk0 = load_k0(t + 1);
+                    // ---- KG independent cell updates ---------------------------------------------------
+                    TFS_TR(1)
+                    const unsigned fl_used = fl;
+                    float a[KG], r[KG], cv[KG], d[KG], pp[KG];
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk) { a[kk] = uL[kk]; r[kk] = uRo[kk]; cv[kk] = vB[kk]; d[kk] = vTo[kk]; pp[kk] = pin[kk]; }
+                    // effective flags of this step: iterations beyond the pass's active count do nothing
+                    unsigned fl_eff = fl_used & FULL;
+                    if (!group_active) {
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk)
+                            if (g * KG + kk >= k_act) fl_eff &= ~(15u << (4 * kk));
+                    }
+                    // per-nibble "is 0 or 15": x ^ (x >> 1 ...) trick: a nibble is uniform iff all 4 bits equal
+                    const unsigned lo = fl_eff & (FULL / 15u);                  // bit 0 of every nibble
+                    const unsigned spread = lo * 15u;                           // 0xF where bit 0 is set
+                    const bool plain_or_off = fl_eff == spread;                 // every nibble is 0x0 or 0xF
+                    const bool all_plain = fl_eff == FULL;
+                    if (__all_sync(0xffffffffu, all_plain)) {
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk)
+                            cell_update4<0>(15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                    } else if (__all_sync(0xffffffffu, plain_or_off)) {
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk)
+                            cell_update4<1>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk)
+                            cell_update4<2>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                    }
+                    // a = uCf (u of the cell after iteration k), r = uRp, cv = vCf, d = vTp, pp = pout
+                    // ---- lane L-1's outputs ---------------------------------------------------------------
+                    TFS_TR(2)
+                    float n_uL[KG], s_v[KG], s_p[KG];
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk) {
+                        n_uL[kk] = __shfl_up_sync(0xffffffffu, r[kk], 1);
+                        s_v[kk] = __shfl_up_sync(0xffffffffu, cv[kk], 1);
+                        s_p[kk] = __shfl_up_sync(0xffffffffu, pp[kk], 1);
+                    }
+                    unsigned s_flv = __shfl_up_sync(0xffffffffu, fl_used, 1);
+                    if (lane == 0) {  // "lane -1" is lane 31 of the left band (zeros where there is none)
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk) {
+                            n_uL[kk] = use_left ? lr[kk].x : 0.0f;
+                            s_v[kk] = use_left ? lr[kk].y : 0.0f;
+                            s_p[kk] = use_left ? lr[kk].z : 0.0f;
+                        }
+                        s_flv = use_left ? __float_as_uint(lr[0].w) : 0u;
+                    }
+                    TFS_TR(3)
+                    // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
+                    s_grp[((t & 1) * NW + g) * 32 + lane] =
+                        make_float4(a[KG - 1], s_v[KG - 1], s_p[KG - 1], __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
+                    if (g == NW - 1) {  // iteration KB-1 retired: final values of the pass -> output stage
+                        so[(0 * 32 + lane) * PITCH + s] = a[KG - 1];
+                        so[(1 * 32 + lane) * PITCH + s] = cv[KG - 1];
+                        so[(2 * 32 + lane) * PITCH + s] = pp[KG - 1];
+                    }
+                    // ---- record of lane 31 for the same k-group of the next band (consumed at the end of ITS step t-32)
+                    {
+                        const int r_out = t - 32;
+                        if (lane == 31 && r_out >= 0 && r_out < P.n_rec) {
+                            float4 *rec_dst = rec_out + (size_t)r_out * KG;
+#pragma unroll
+                            for (int kk = 0; kk < KG; ++kk)
+                                rec_dst[kk] = make_float4(r[kk], cv[kk], pp[kk], kk == 0 ? __uint_as_float(fl_used) : 0.0f);
+                        }
+                    }
+                    // ---- operands of step t+1 (in-group part) ------------------------------------------------
+#pragma unroll
+                    for (int kk = KG - 1; kk >= 0; --kk) {
+                        vB[kk] = d[kk];
+                        uL[kk] = n_uL[kk];
+                        if (kk >= 1) {
+                            uRo[kk] = a[kk - 1];
+                            vTo[kk] = s_v[kk - 1];
+                            pin[kk] = pd[kk];  // filled at the end of step t-1 (two-step path)
+                            pd[kk] = s_p[kk - 1];
+                        }
+                    }
+                    fl = fld;           // flags: two-step path; slot 0 is set below
+                    fld = s_flv << 4;   // (used at t by lane L-1, needed at t+2 by lane L one slot higher)
+                    TFS_TR(4)
+                    bar_sync_imm<BAR_STEP, NCT>();
+                    TFS_TR(5)
+                    if (g > 0) {
+                        const float4 gi = s_grp[((t & 1) * NW + (g - 1)) * 32 + lane];
+                        uRo[0] = gi.x;
+                        vTo[0] = gi.y;
+                        pin[0] = pd[0];
+                        pd[0] = gi.z;
+                        fld |= __float_as_uint(gi.w);  // the nibble for slot 0, two steps from now
+                    } else if (have_next) {
+                        apply_k0(t + 1, nk0);
+                    }
+                }
+                bar_arrive2<BAR_FREE0, NALL>(c);  // stage, ring and output slots of chunk c are done
+            }
+#ifdef TFS_SYS_TRACE
+            if (lane == 0 && P.trace) {
+                for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[(g * 8 + i)], (unsigned long long)tr_acc[i]);
+            }
+#endif
         }
-        // ---- epilogue: last partial chunk, final progress ----------------------------------------------------
-        cp_async_wait<0>();
-        __syncthreads();
-        if (P.T % S != 0) flush_out((P.T / S) * S, P.T - 1);
-        fence_gpu();
-        __syncthreads();
-        if (threadIdx.x == 0) st_volatile(my_out_prog, (int)H);
-        if (lane == 31) st_volatile(my_prog, P.n_rec);
     }
 }
 
@@ -405,8 +533,8 @@ struct SysLaunch {
     static size_t smem_bytes() {
         constexpr int PITCH = S + 1, FW = ((S + 4 + 3) / 4) | 1;
         return sizeof(float) * (size_t)(2 * 3 * 32 * PITCH) + sizeof(unsigned) * (size_t)(2 * 32 * FW) +
-               sizeof(float) * (size_t)(3 * 32 * PITCH) + sizeof(float4) * (size_t)(2 * NW * 32) +
-               sizeof(float4) * (size_t)(NW * (D + 1) * KG) + sizeof(float4) * (size_t)KG;
+               sizeof(float) * (size_t)(2 * 3 * 32 * PITCH) + sizeof(float4) * (size_t)(2 * NW * 32) +
+               sizeof(float4) * (size_t)(2 * NW * S * KG);
     }
     static cudaError_t run(const SystolicArgs &a, SystolicWorkspace &ws, uint64_t *launched, const char **msg) {
         cudaError_t e;
@@ -430,7 +558,7 @@ struct SysLaunch {
         P.buf[1][0] = *a.u2; P.buf[1][1] = *a.v2; P.buf[1][2] = *a.p2;
         // workspace: records [2][n_bands][NW][n_rec][KG] float4, then counters
         const size_t rec_bytes = (size_t)2 * P.n_bands * NW * P.n_rec * KG * sizeof(float4);
-        const size_t n_prog = (size_t)P.n_passes * P.n_bands * NW;
+        const size_t n_prog = (size_t)P.n_passes * P.n_bands;
         const size_t n_out = (size_t)P.n_passes * P.n_bands;
         const size_t n_cnt = n_prog + n_out + 16;
         const size_t need = rec_bytes + n_cnt * sizeof(int);
@@ -446,6 +574,13 @@ struct SysLaunch {
         P.bnd_prog = cnt;
         P.out_prog = cnt + n_prog;
         P.ticket = cnt + n_prog + n_out;
+        P.trace = nullptr;
+#ifdef TFS_SYS_TRACE
+        static long long *d_trace = nullptr;
+        if (!d_trace) cudaMalloc((void **)&d_trace, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), a.stream);
+        P.trace = d_trace;
+#endif
         if ((e = cudaMemsetAsync(cnt, 0, n_cnt * sizeof(int), a.stream)) != cudaSuccess) return e;
         auto kern = k_project_systolic<KG, NW, S, D>;
         const size_t smem = smem_bytes();
@@ -456,15 +591,36 @@ struct SysLaunch {
                 *msg = "cudaFuncSetAttribute(max dynamic smem)";
                 return e;
             }
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, smem)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (NW + 1), smem)) != cudaSuccess) return e;
             attr_set = true;
         }
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
         const long long n_tasks = (long long)P.n_passes * P.n_bands;
         const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
-        kern<<<grid, 32 * NW, smem, a.stream>>>(P);
+        kern<<<grid, 32 * (NW + 1), smem, a.stream>>>(P);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
+#ifdef TFS_SYS_TRACE
+        {
+            long long h[64 * 8];
+            cudaStreamSynchronize(a.stream);
+            cudaMemcpy(h, P.trace, sizeof(h), cudaMemcpyDeviceToHost);
+            const double nsteps = (double)P.T * n_tasks;
+            const char *names[8] = {"loop/other", "early loads", "updates", "shuffles+patch", "stores+shift", "STEP barrier", "READY barrier", "-"};
+            {
+                const char *ion[8] = {"prologue", "wait FREE", "flush", "fence+publish", "wait deps", "acq fence", "issue", "cp wait"};
+                const double nchunks = (double)((P.T + S - 1) / S) * n_tasks;
+                fprintf(stderr, "[trace] IO warp cycles/chunk:");
+                for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", ion[i], h[NW * 8 + i] / nchunks);
+                fprintf(stderr, "\n");
+            }
+            for (int gq = 0; gq < 1; ++gq) {
+                fprintf(stderr, "[trace] warp %d cycles/step:", gq);
+                for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], h[gq * 8 + i] / nsteps);
+                fprintf(stderr, "\n");
+            }
+        }
+#endif
         if (P.n_passes & 1) {  // results are in set 1
             std::swap(*a.u, *a.u2);
             std::swap(*a.v, *a.v2);
@@ -517,6 +673,13 @@ inline SysShape systolic_pick(int iterations, int requested) {
 
 inline cudaError_t systolic_project(const SystolicArgs &a, SystolicWorkspace &ws, uint64_t *launched, const char **msg) {
     const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
+    const char *env_s = getenv("TFS_SYS_S");
+    const int S_ = env_s ? atoi(env_s) : 16;
+    if (S_ == 8 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 8, 6>::run(a, ws, launched, msg);
+    if (S_ == 8 && sh.kg == 2 && sh.nw == 8) return SysLaunch<2, 8, 8, 6>::run(a, ws, launched, msg);
+    if (S_ == 32 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 32, 6>::run(a, ws, launched, msg);
+    if (S_ == 64 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 64, 6>::run(a, ws, launched, msg);
+    if (S_ == 64 && sh.kg == 1 && sh.nw == 8) return SysLaunch<1, 8, 64, 6>::run(a, ws, launched, msg);
 #define TFS_SYS_CASE(KG_, NW_) \
     if (sh.kg == KG_ && sh.nw == NW_) return SysLaunch<KG_, NW_, 16, 6>::run(a, ws, launched, msg);
     TFS_SYS_CASE(4, 4)
