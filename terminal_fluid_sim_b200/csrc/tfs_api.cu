@@ -13,6 +13,7 @@
 #include "../../include/tfs.h"
 #include "tfs_kernels.cuh"
 #include "tfs_systolic.cuh"
+#include "tfs_systolic4.cuh"
 
 #define TFS_VERSION_STRING "tfs-cuda 0.1.0 (sm_100a)"
 
@@ -63,6 +64,7 @@ struct tfs_sim {
     void *d_stage = nullptr;  // view packing
     size_t stage_bytes = 0;
     tfs::SystolicWorkspace sys;
+    tfs::Systolic4Workspace sys4;
     // measurement
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profiling = false;
@@ -252,7 +254,7 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
         a.stream = s->stream;
         const char *msg = nullptr;
         uint64_t launched = 0;
-        cudaError_t e = tfs::systolic_project(a, s->sys, &launched, &msg);
+        cudaError_t e = tfs::systolic_project_auto(a, s->sys, s->sys4, &launched, &msg);
         s->launches += launched;
         if (e != cudaSuccess)
             return fail(e == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "systolic projection: %s (%s)",
@@ -435,6 +437,7 @@ int tfs_destroy(tfs_sim *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     free_fields(s);
     tfs::systolic_release(s->sys);
+    tfs::systolic4_release(s->sys4);
     if (s->d_part) cudaFree(s->d_part);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->d_stage) cudaFree(s->d_stage);

@@ -1,0 +1,555 @@
+// tfs_systolic4.cuh -- the production variant of the systolic wavefront projection (H % 4 == 0).
+//
+// Same schedule and arithmetic as tfs_systolic.cuh (see its header and oracle/systolic_model.py);
+// what changes is how data moves between HBM and the pipeline:
+//   * warp roles: NW compute warps (k-groups), one LOADER warp, one STORER warp.  Every wait on
+//     global memory (progress counters of other CTAs), every fence and every bulk copy lives in the
+//     two IO warps; compute warps only touch registers, shared memory and shared-memory mbarriers.
+//   * k = 0 operands come from rectangular 32-column x 32-row blocks (one 128-byte line per column
+//     and field), copied global -> shared with 16-byte cp.async.cg (bypasses L1: no stale lines)
+//     into a 3-slot ring; lane l reads row tau - l - 1, i.e. bank (tau - l - 1) & 31: conflict-free.
+//   * final values are written into a 3-slot ring of 32 x 32 blocks and stored with 128-bit
+//     coalesced stores once the last lane has retired the block's last row.
+//   * the left band's records are prefetched per interval of G steps (not per chunk), published by
+//     the producer's storer warp every G steps, so a band trails its left neighbour by ~32 + 2G
+//     steps; all hand-offs inside the CTA are mbarrier full/empty pairs.
+//   * tasks are issued in dependency-respecting "start time" order (host-sorted list).
+#pragma once
+#include <utility>
+#include <vector>
+
+#include "tfs_systolic.cuh"
+
+namespace tfs {
+
+TFS_DEVINL unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+TFS_DEVINL void mbar_init(unsigned long long *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+TFS_DEVINL void mbar_arrive(unsigned long long *b) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(b)) : "memory");
+}
+// arrive once all cp.async issued so far by this thread have landed (counts as one expected arrival)
+TFS_DEVINL void mbar_arrive_on_cp_async(unsigned long long *b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+TFS_DEVINL void mbar_wait(unsigned long long *b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" ::"r"(
+            smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+
+struct Sys4Params {
+    SysParams base;
+    const int2 *tasks;  // (pass, band) in issue order
+};
+
+template <int KG, int NW, int G>
+struct Sys4Smem {
+    static constexpr int NS_IN = 3, NS_OUT = 3, NR = 3, NPH = 4;
+    float in_u[NS_IN][32][32];
+    float in_v[NS_IN][32][32];
+    float in_p[NS_IN][32][32];
+    float out_u[NS_OUT][32][32];
+    float out_v[NS_OUT][32][32];
+    float out_p[NS_OUT][32][32];
+    float4 grp[2][NW][32];
+    float4 rec[NR][NW][G][KG];
+    unsigned char in_f[NS_IN][32][32];
+    unsigned long long in_full[NS_IN], in_empty[NS_IN];
+    unsigned long long rec_full[NR], rec_empty[NR];
+    unsigned long long rec_written[NPH], pub_done[NPH];
+    unsigned long long out_empty[NS_OUT];
+    int task;
+};
+
+template <int KG, int NW, int G>
+__global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params P4) {
+    using SM = Sys4Smem<KG, NW, G>;
+    constexpr int KB = KG * NW;
+    constexpr int NCT = 32 * NW;
+    constexpr int NS_IN = SM::NS_IN, NS_OUT = SM::NS_OUT, NR = SM::NR, NPH = SM::NPH;
+    static_assert(32 % G == 0, "a 32-row block is a whole number of record intervals");
+    static_assert(KG >= 1 && KG <= 8, "a k-group's flags are packed 4 bits per iteration into 32 bits");
+    const SysParams &P = P4.base;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const bool is_loader = g == NW, is_storer = g == NW + 1;
+    const long long W = P.W, H = P.H;
+    const int n_tasks = P.n_passes * P.n_bands;
+
+    for (;;) {
+        __syncthreads();  // previous task fully retired (smem and mbarrier reuse)
+        if (threadIdx.x == 0) {
+            sm.task = atomicAdd(P.ticket, 1);
+            for (int i = 0; i < NS_IN; ++i) { mbar_init(&sm.in_full[i], 32); mbar_init(&sm.in_empty[i], 1); }
+            for (int i = 0; i < NR; ++i) { mbar_init(&sm.rec_full[i], 32); mbar_init(&sm.rec_empty[i], NW); }
+            for (int i = 0; i < NPH; ++i) { mbar_init(&sm.rec_written[i], NW); mbar_init(&sm.pub_done[i], 1); }
+            for (int i = 0; i < NS_OUT; ++i) mbar_init(&sm.out_empty[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        const int ticket = sm.task;
+        if (ticket >= n_tasks) break;
+        const int2 tk = P4.tasks[ticket];
+        const int tb = tk.x, b = tk.y;
+        const int k_act = (tb == P.n_passes - 1) ? P.k_last : KB;
+        const bool first_pass = tb == 0;
+        const long long q0 = (long long)b * 32 - 1;  // skewed coordinate of lane 0
+        const bool has_left = b > 0;
+        const size_t rec_stride = (size_t)P.n_rec * KG;  // float4 per (band, k-group)
+        const int T = P.T;
+        const int n_int = (T + G - 1) / G;                 // record intervals
+        const int n_blk_in = (int)((H + 31) >> 5);          // field blocks that hold real rows
+        const int m_last = (int)((H - 1) >> 5);             // last output block
+
+        if (is_loader) {
+            // ===================================== LOADER ===========================================
+            const float *__restrict__ gin_u = P.buf[tb & 1][0];
+            const float *__restrict__ gin_v = P.buf[tb & 1][1];
+            const float *__restrict__ gin_p = P.buf[tb & 1][2];
+            const float4 *rec_in = P.bnd + ((size_t)(tb & 1) * P.n_bands + (b - 1)) * NW * rec_stride;
+            const int *left_prog = P.bnd_prog + (size_t)tb * P.n_bands + (b - 1);
+            const int *dep_out0 = P.out_prog + (size_t)(tb - 1) * P.n_bands + b;
+            const int *dep_out1 = P.out_prog + (size_t)(tb - 1) * P.n_bands + min(b + 1, P.n_bands - 1);
+            int known_left = 0, known_rows = first_pass ? (int)H : 0;
+
+            auto load_block = [&](int n) {
+                // rows [32n, 32n+32) of columns q0.. (u: q0+1..) -> slot n % NS_IN
+                const int slot = n % NS_IN;
+                mbar_wait(&sm.in_empty[slot], ((n / NS_IN) & 1) ^ 1);
+                int need = 32 * n + 32;
+                if (need > (int)H) need = (int)H;
+                if (known_rows < need) {
+                    do {
+                        int k0 = 0;
+                        if (lane == 0) k0 = min(ld_volatile(dep_out0), ld_volatile(dep_out1));
+                        known_rows = __shfl_sync(0xffffffffu, k0, 0);
+                    } while (known_rows < need);
+                    fence_gpu();  // acquire
+                }
+                if (n < n_blk_in) {
+                    const long long row0 = 32LL * n;
+                    const int part = lane & 7;  // 16-byte piece of the column's 128-byte line
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int cc = it * 4 + (lane >> 3);
+                        const long long col = q0 + cc;
+                        if (col + 1 >= 0 && col + 1 < W)
+                            cp_async16_cg(&sm.in_u[slot][cc][part * 4], gin_u + (col + 1) * H + row0 + part * 4);
+                        if (col >= 0 && col < W) {
+                            cp_async16_cg(&sm.in_v[slot][cc][part * 4], gin_v + col * H + row0 + part * 4);
+                            if (!first_pass) cp_async16_cg(&sm.in_p[slot][cc][part * 4], gin_p + col * H + row0 + part * 4);
+                            cp_async4(&sm.in_f[slot][cc][part * 4], P.flags + col * H + row0 + part * 4);  // static data: L1 is fine
+                        }
+                    }
+                }
+                mbar_arrive_on_cp_async(&sm.in_full[slot]);
+            };
+            auto load_records = [&](int j) {
+                const int slot = j % NR;
+                mbar_wait(&sm.rec_empty[slot], ((j / NR) & 1) ^ 1);
+                if (has_left) {
+                    int need = (j + 1) * G;
+                    if (need > P.n_rec) need = P.n_rec;
+                    if (known_left < need) {
+                        do {
+                            int k0 = 0;
+                            if (lane == 0) k0 = ld_volatile(left_prog);
+                            known_left = __shfl_sync(0xffffffffu, k0, 0);
+                        } while (known_left < need);
+                        fence_gpu();  // acquire
+                    }
+                    float4 *dst = &sm.rec[slot][0][0][0];
+                    for (int e = lane; e < NW * G * KG; e += 32) {
+                        const int gg = e / (G * KG), x = e % (G * KG);
+                        long long r4 = (long long)j * G * KG + x;  // float4 index inside the group's stream
+                        if (r4 >= (long long)rec_stride) r4 = (long long)rec_stride - 1;  // past the end: masked at use
+                        cp_async16_cg(dst + e, rec_in + (size_t)gg * rec_stride + r4);
+                    }
+                }
+                mbar_arrive_on_cp_async(&sm.rec_full[slot]);
+            };
+
+            const int n_blk_needed = ((T - 1) >> 5) + 1;  // blocks the compute warps will wait for
+            load_block(0);
+            for (int j = 0; j < n_int; ++j) {
+                load_records(j);
+                if ((j * G) % 32 == 0) {
+                    const int n = (j * G) / 32 + 1;  // one block ahead of the compute warps
+                    if (n < n_blk_needed) load_block(n);
+                }
+            }
+        } else if (is_storer) {
+            // ===================================== STORER ===========================================
+            float *__restrict__ gout_u = P.buf[(tb + 1) & 1][0];
+            float *__restrict__ gout_v = P.buf[(tb + 1) & 1][1];
+            float *__restrict__ gout_p = P.buf[(tb + 1) & 1][2];
+            int *my_prog = P.bnd_prog + (size_t)tb * P.n_bands + b;
+            int *my_out_prog = P.out_prog + (size_t)tb * P.n_bands + b;
+            int m_next = 0, rows_done = 0;
+            // block m (rows [32m, 32m+32)) is complete once lane 31 retired its last row
+            auto done_step = [&](int m) { return min(32 * m + 62 + KB, T - 1); };
+            auto store_block = [&](int m) {
+                const int slot = m % NS_OUT;
+                const long long row0 = 32LL * m;
+                const int part = lane & 7;
+                if (row0 + part * 4 < H) {  // H % 4 == 0: a float4 is entirely inside or outside the column
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int cc = it * 4 + (lane >> 3);
+                        const long long col = q0 + cc - (KB - 1);
+                        if (col >= 0 && col < W) {
+                            const long long idx = col * H + row0 + part * 4;
+                            *reinterpret_cast<float4 *>(gout_u + idx) = *reinterpret_cast<const float4 *>(&sm.out_u[slot][cc][part * 4]);
+                            *reinterpret_cast<float4 *>(gout_v + idx) = *reinterpret_cast<const float4 *>(&sm.out_v[slot][cc][part * 4]);
+                            *reinterpret_cast<float4 *>(gout_p + idx) = *reinterpret_cast<const float4 *>(&sm.out_p[slot][cc][part * 4]);
+                        }
+                    }
+                }
+            };
+            for (int j = 0; j < n_int; ++j) {
+                mbar_wait(&sm.rec_written[j % NPH], (j / NPH) & 1);  // steps < (j+1)*G retired by every k-group
+                const int t_done = min((j + 1) * G, T) - 1;
+                int m_first = m_next;
+                while (m_next <= m_last && done_step(m_next) <= t_done) { store_block(m_next); ++m_next; }
+                __syncwarp();
+                fence_gpu();  // release: block stores above + the records the compute warps wrote
+                if (lane == 0) {
+                    int recs = t_done - 32 + 1;
+                    recs = recs < 0 ? 0 : (recs > P.n_rec ? P.n_rec : recs);
+                    if (j == n_int - 1) recs = P.n_rec;
+                    st_volatile(my_prog, recs);
+                    if (m_next != m_first) {
+                        rows_done = min(32 * m_next, (int)H);
+                        st_volatile(my_out_prog, rows_done);
+                    }
+                    for (int m = m_first; m < m_next; ++m) mbar_arrive(&sm.out_empty[m % NS_OUT]);
+                    mbar_arrive(&sm.pub_done[j % NPH]);
+                }
+            }
+        } else {
+            // ================================== compute warps =========================================
+            const bool grav = first_pass && P.apply_gravity;
+            const long long q = q0 + lane;
+            float4 *rec_out = P.bnd + (((size_t)(tb & 1) * P.n_bands + b) * NW + g) * rec_stride;
+            const bool col_ok = q >= 0 && q < W;
+            const bool colp_ok = q + 1 >= 0 && q + 1 < W;
+
+            float uL[KG], uRo[KG], vB[KG], vTo[KG], pin[KG], pd[KG];
+#pragma unroll
+            for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
+            unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
+
+            // k = 0 operands of step tau: u[q+1, rho], p[q, rho], flags[q, rho], v[q, rho+1], flags[q, rho+1]
+            // with rho = tau - lane - 1, read from the block ring (k-group 0 only)
+            struct K0 { float su, sv, sp; unsigned f0, f1; };
+            auto load_k0 = [&](int tau) -> K0 {
+                const int rho = tau - lane - 1, rho1 = rho + 1;
+                const int blk = rho < 0 ? 0 : (rho >> 5), blk1 = rho1 < 0 ? 0 : (rho1 >> 5);
+                const int s0 = blk % NS_IN, s1 = blk1 % NS_IN;
+                K0 o;
+                o.su = sm.in_u[s0][lane][rho & 31];
+                o.sp = sm.in_p[s0][lane][rho & 31];
+                o.f0 = sm.in_f[s0][lane][rho & 31];
+                o.sv = sm.in_v[s1][lane][rho1 & 31];
+                o.f1 = sm.in_f[s1][lane][rho1 & 31];
+                return o;
+            };
+            auto apply_k0 = [&](int tau, const K0 &o) {
+                const long long row = (long long)tau - lane - 1;
+                const bool row_ok = row >= 0 && row < H;
+                const bool rowp_ok = row + 1 >= 0 && row + 1 < H;
+                const unsigned f0 = (col_ok && row_ok) ? o.f0 : 0u;
+                const unsigned f1 = (col_ok && rowp_ok) ? o.f1 : 0u;
+                uRo[0] = (colp_ok && row_ok) ? o.su : 0.0f;
+                float vv = (col_ok && rowp_ok) ? o.sv : 0.0f;
+                if (grav && (f1 & TFS_F_LIVE)) vv = fadd(vv, P.gdt);  // simulator.rs:147
+                vTo[0] = vv;
+                pin[0] = (!first_pass && col_ok && row_ok) ? o.sp : 0.0f;
+                fl = (fl & ~0xFu) | (f0 & 15u);
+            };
+            // the first use of input block n: wait for it, and release block n-2 (its rows are behind lane 31)
+            auto acquire_in_block = [&](int n) {
+                mbar_wait(&sm.in_full[n % NS_IN], (n / NS_IN) & 1);
+                if (n >= 2) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.in_empty[(n - 2) % NS_IN]);
+                }
+            };
+            constexpr unsigned FULL = (KG == 8) ? 0xFFFFFFFFu : ((1u << (4 * KG)) - 1u);
+            const bool group_active = (g + 1) * KG <= k_act;  // every iteration of this k-group runs in this pass
+
+            if (g == 0) {
+                acquire_in_block(0);
+                apply_k0(0, load_k0(0));
+            }
+            for (int t = 0; t < T; ++t) {
+                const int j = t / G, sg = t % G;  // record interval, step inside it
+                if (sg == 0) {
+                    mbar_wait(&sm.rec_full[j % NR], (j / NR) & 1);
+                    if (g == NW - 1) {
+                        // lane 0 is about to touch output block m = (t - KB) / 32 for the first time
+                        // (first touch of block m happens at step 32m + KB: wait if it falls in this interval)
+                        const int tt = t - KB;
+                        const int m = (tt + 31) >> 5;
+                        if (m >= NS_OUT && 32 * m - tt < G) mbar_wait(&sm.out_empty[m % NS_OUT], ((m / NS_OUT) & 1) ^ 1);
+                    }
+                }
+                const bool use_left = has_left && t < P.n_rec;
+                // ---- early loads: left band's record (for lane 0) and next step's k = 0 operands
+                float4 lr[KG];
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) lr[kk] = sm.rec[j % NR][g][sg][kk];  // broadcast read
+                const bool have_next = (g == 0) && (t + 1 < T);
+                K0 nk0 = {0.f, 0.f, 0.f, 0u, 0u};
+                if (have_next) {
+                    if (((t + 1) & 31) == 0) acquire_in_block((t + 1) >> 5);
+                    nk0 = load_k0(t + 1);
+                }
+                // ---- KG independent cell updates ---------------------------------------------------
+                const unsigned fl_used = fl;
+                float a[KG], r[KG], cv[KG], d[KG], pp[KG];
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) { a[kk] = uL[kk]; r[kk] = uRo[kk]; cv[kk] = vB[kk]; d[kk] = vTo[kk]; pp[kk] = pin[kk]; }
+                unsigned fl_eff = fl_used & FULL;
+                if (!group_active) {
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk)
+                        if (g * KG + kk >= k_act) fl_eff &= ~(15u << (4 * kk));
+                }
+                const unsigned spread = (fl_eff & (FULL / 15u)) * 15u;  // 0xF where bit 0 of the nibble is set
+                const bool plain_or_off = fl_eff == spread;            // every nibble is 0x0 or 0xF
+                const bool all_plain = fl_eff == FULL;
+                if (__all_sync(0xffffffffu, all_plain)) {
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk)
+                        cell_update4<0>(15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                } else if (__all_sync(0xffffffffu, plain_or_off)) {
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk)
+                        cell_update4<1>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk)
+                        cell_update4<2>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                }
+                // a = uCf (u of the cell after iteration k), r = uRp, cv = vCf, d = vTp, pp = pout
+                // ---- lane L-1's outputs ---------------------------------------------------------------
+                float n_uL[KG], s_v[KG], s_p[KG];
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) {
+                    n_uL[kk] = __shfl_up_sync(0xffffffffu, r[kk], 1);
+                    s_v[kk] = __shfl_up_sync(0xffffffffu, cv[kk], 1);
+                    s_p[kk] = __shfl_up_sync(0xffffffffu, pp[kk], 1);
+                }
+                unsigned s_flv = __shfl_up_sync(0xffffffffu, fl_used, 1);
+                if (lane == 0) {  // "lane -1" is lane 31 of the left band (zeros where there is none)
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk) {
+                        n_uL[kk] = use_left ? lr[kk].x : 0.0f;
+                        s_v[kk] = use_left ? lr[kk].y : 0.0f;
+                        s_p[kk] = use_left ? lr[kk].z : 0.0f;
+                    }
+                    s_flv = use_left ? __float_as_uint(lr[0].w) : 0u;
+                }
+                // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
+                sm.grp[t & 1][g][lane] =
+                    make_float4(a[KG - 1], s_v[KG - 1], s_p[KG - 1], __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
+                if (g == NW - 1) {  // iteration KB-1 retired: final values of cell (q-(KB-1), t-lane-KB) -> output ring
+                    const int rho = t - lane - KB;
+                    if (rho >= 0) {
+                        const int slot = (rho >> 5) % NS_OUT;
+                        sm.out_u[slot][lane][rho & 31] = a[KG - 1];
+                        sm.out_v[slot][lane][rho & 31] = cv[KG - 1];
+                        sm.out_p[slot][lane][rho & 31] = pp[KG - 1];
+                    }
+                }
+                // ---- record of lane 31 for the same k-group of the next band (consumed at the end of ITS step t-32)
+                {
+                    const int r_out = t - 32;
+                    if (lane == 31 && r_out >= 0 && r_out < P.n_rec) {
+                        float4 *rec_dst = rec_out + (size_t)r_out * KG;
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk)
+                            rec_dst[kk] = make_float4(r[kk], cv[kk], pp[kk], kk == 0 ? __uint_as_float(fl_used) : 0.0f);
+                    }
+                }
+                // ---- operands of step t+1 (in-group part) ------------------------------------------------
+#pragma unroll
+                for (int kk = KG - 1; kk >= 0; --kk) {
+                    vB[kk] = d[kk];
+                    uL[kk] = n_uL[kk];
+                    if (kk >= 1) {
+                        uRo[kk] = a[kk - 1];
+                        vTo[kk] = s_v[kk - 1];
+                        pin[kk] = pd[kk];  // filled at the end of step t-1 (two-step path)
+                        pd[kk] = s_p[kk - 1];
+                    }
+                }
+                fl = fld;           // flags: two-step path; slot 0 is set below
+                fld = s_flv << 4;   // (used at t by lane L-1, needed at t+2 by lane L one slot higher)
+                // ---- end of a record interval: hand the slot back, tell the storer the records are written
+                if (sg == G - 1 || t == T - 1) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&sm.rec_empty[j % NR]);
+                        if (j >= NPH) mbar_wait(&sm.pub_done[j % NPH], ((j / NPH) & 1) ^ 1);
+                        mbar_arrive(&sm.rec_written[j % NPH]);
+                    }
+                }
+                bar_sync_imm<BAR_STEP, NCT>();
+                if (g > 0) {
+                    const float4 gi = sm.grp[t & 1][g - 1][lane];
+                    uRo[0] = gi.x;
+                    vTo[0] = gi.y;
+                    pin[0] = pd[0];
+                    pd[0] = gi.z;
+                    fld |= __float_as_uint(gi.w);  // the nibble for slot 0, two steps from now
+                } else if (have_next) {
+                    apply_k0(t + 1, nk0);
+                }
+            }
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+struct Systolic4Workspace {
+    int2 *d_tasks = nullptr;
+    size_t n_tasks_cap = 0;
+    long long key_W = -1, key_H = -1;
+    int key_passes = -1, key_bands = -1;
+};
+
+template <int KG, int NW, int G>
+struct Sys4Launch {
+    static constexpr int KB = KG * NW;
+    static cudaError_t run(const SystolicArgs &a, SystolicWorkspace &ws, Systolic4Workspace &ws4, uint64_t *launched,
+                           const char **msg) {
+        cudaError_t e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if (ws.num_sms == 0) {
+            if ((e = cudaDeviceGetAttribute(&ws.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        }
+        const int K = a.iterations;
+        Sys4Params P4{};
+        SysParams &P = P4.base;
+        P.W = a.W; P.H = a.H; P.ncells = a.W * a.H;
+        P.n_passes = (K + KB - 1) / KB;
+        P.k_last = K - (P.n_passes - 1) * KB;
+        P.n_bands = (int)((a.W + KB + 31) / 32);
+        P.T = (int)a.H + 32 + KB;
+        P.n_rec = (int)a.H + KB;
+        P.apply_gravity = a.fuse_gravity ? 1 : 0;
+        P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
+        P.flags = a.flags;
+        P.buf[0][0] = *a.u; P.buf[0][1] = *a.v; P.buf[0][2] = *a.p;
+        P.buf[1][0] = *a.u2; P.buf[1][1] = *a.v2; P.buf[1][2] = *a.p2;
+        P.trace = nullptr;
+        const size_t rec_bytes = (size_t)2 * P.n_bands * NW * P.n_rec * KG * sizeof(float4);
+        const size_t n_prog = (size_t)P.n_passes * P.n_bands;
+        const size_t n_cnt = 2 * n_prog + 16;
+        const size_t need = rec_bytes + n_cnt * sizeof(int);
+        if (ws.bytes < need) {
+            if (ws.buf) cudaFree(ws.buf);
+            ws.buf = nullptr;
+            ws.bytes = 0;
+            if ((e = cudaMalloc(&ws.buf, need)) != cudaSuccess) { *msg = "workspace allocation"; return e; }
+            ws.bytes = need;
+        }
+        P.bnd = reinterpret_cast<float4 *>(ws.buf);
+        int *cnt = reinterpret_cast<int *>(reinterpret_cast<char *>(ws.buf) + rec_bytes);
+        P.bnd_prog = cnt;
+        P.out_prog = cnt + n_prog;
+        P.ticket = cnt + 2 * n_prog;
+        if ((e = cudaMemsetAsync(cnt, 0, n_cnt * sizeof(int), a.stream)) != cudaSuccess) return e;
+        // task list in "start time" order: a band trails its left neighbour by ~lag_b steps and the
+        // same band of the previous pass by ~lag_t steps; every dependency has a strictly smaller key.
+        const long long n_tasks = (long long)P.n_passes * P.n_bands;
+        if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands) {
+            const int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
+            std::vector<std::pair<long long, int2>> v;
+            v.reserve((size_t)n_tasks);
+            for (int tb = 0; tb < P.n_passes; ++tb)
+                for (int b = 0; b < P.n_bands; ++b) v.push_back({(long long)b * lag_b + (long long)tb * lag_t, make_int2(tb, b)});
+            std::stable_sort(v.begin(), v.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+            std::vector<int2> order((size_t)n_tasks);
+            for (size_t i = 0; i < v.size(); ++i) order[i] = v[i].second;
+            if (ws4.n_tasks_cap < (size_t)n_tasks) {
+                if (ws4.d_tasks) cudaFree(ws4.d_tasks);
+                ws4.d_tasks = nullptr;
+                ws4.n_tasks_cap = 0;
+                if ((e = cudaMalloc((void **)&ws4.d_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
+                ws4.n_tasks_cap = (size_t)n_tasks;
+            }
+            if ((e = cudaMemcpyAsync(ws4.d_tasks, order.data(), (size_t)n_tasks * sizeof(int2), cudaMemcpyHostToDevice, a.stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(a.stream)) != cudaSuccess) return e;  // `order` is a local
+            ws4.key_W = a.W; ws4.key_H = a.H; ws4.key_passes = P.n_passes; ws4.key_bands = P.n_bands;
+        }
+        P4.tasks = ws4.d_tasks;
+        auto kern = k_project_systolic4<KG, NW, G>;
+        const size_t smem = sizeof(Sys4Smem<KG, NW, G>) + 128;
+        static bool attr_set = false;
+        static int occ = 0;
+        if (!attr_set) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
+                *msg = "cudaFuncSetAttribute(max dynamic smem)";
+                return e;
+            }
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (NW + 2), smem)) != cudaSuccess) return e;
+            attr_set = true;
+        }
+        if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
+        const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
+        kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
+        if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
+        *launched += 1;
+        if (P.n_passes & 1) {  // results are in set 1
+            std::swap(*a.u, *a.u2);
+            std::swap(*a.v, *a.v2);
+            std::swap(*a.p, *a.p2);
+        }
+        return cudaSuccess;
+    }
+};
+
+inline void systolic4_release(Systolic4Workspace &ws4) {
+    if (ws4.d_tasks) cudaFree(ws4.d_tasks);
+    ws4.d_tasks = nullptr;
+    ws4.n_tasks_cap = 0;
+    ws4.key_W = ws4.key_H = -1;
+}
+
+// H % 4 == 0: the block-ring kernel; otherwise the generic cp.async-4 kernel of tfs_systolic.cuh
+inline cudaError_t systolic_project_auto(const SystolicArgs &a, SystolicWorkspace &ws, Systolic4Workspace &ws4,
+                                         uint64_t *launched, const char **msg) {
+    const char *force_v3 = getenv("TFS_SYS_V3");
+    if ((a.H % 4) != 0 || (force_v3 && atoi(force_v3))) return systolic_project(a, ws, launched, msg);
+    const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
+    const char *env_g = getenv("TFS_SYS_G");
+    const int G_ = env_g ? atoi(env_g) : 8;
+#define TFS_SYS4_CASE(KG_, NW_)                                                                          \
+    if (sh.kg == KG_ && sh.nw == NW_) {                                                                  \
+        if (G_ == 4) return Sys4Launch<KG_, NW_, 4>::run(a, ws, ws4, launched, msg);                     \
+        return Sys4Launch<KG_, NW_, 8>::run(a, ws, ws4, launched, msg);                                  \
+    }
+    TFS_SYS4_CASE(4, 4)
+    TFS_SYS4_CASE(2, 8)
+    TFS_SYS4_CASE(4, 2)
+    TFS_SYS4_CASE(2, 4)
+    TFS_SYS4_CASE(4, 3)
+    TFS_SYS4_CASE(2, 5)
+    TFS_SYS4_CASE(4, 8)
+#undef TFS_SYS4_CASE
+    return systolic_project(a, ws, launched, msg);
+}
+
+}  // namespace tfs
