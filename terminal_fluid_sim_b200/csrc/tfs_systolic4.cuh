@@ -49,15 +49,16 @@ struct Sys4Params {
 template <int KG, int NW, int G>
 struct Sys4Smem {
     static constexpr int NS_IN = 3, NS_OUT = 3, NR = 3, NPH = 4;
-    float in_u[NS_IN][32][32];
-    float in_v[NS_IN][32][32];
-    float in_p[NS_IN][32][32];
-    float out_u[NS_OUT][32][32];
-    float out_v[NS_OUT][32][32];
-    float out_p[NS_OUT][32][32];
+    // row rings: [column][slot*32 + row-in-block]; 32*NS rows per column, bank = row & 31
+    float in_u[32][32 * NS_IN];
+    float in_v[32][32 * NS_IN];
+    float in_p[32][32 * NS_IN];
+    float out_u[32][32 * NS_OUT];
+    float out_v[32][32 * NS_OUT];
+    float out_p[32][32 * NS_OUT];
     float4 grp[2][NW][32];
     float4 rec[NR][NW][G][KG];
-    unsigned char in_f[NS_IN][32][32];
+    unsigned char in_f[32][32 * NS_IN + 4];  // +4: odd word pitch, fewer bank conflicts on the diagonal byte reads
     unsigned long long in_full[NS_IN], in_empty[NS_IN];
     unsigned long long rec_full[NR], rec_empty[NR];
     unsigned long long rec_written[NPH], pub_done[NPH];
@@ -141,11 +142,11 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                         const int cc = it * 4 + (lane >> 3);
                         const long long col = q0 + cc;
                         if (col + 1 >= 0 && col + 1 < W)
-                            cp_async16_cg(&sm.in_u[slot][cc][part * 4], gin_u + (col + 1) * H + row0 + part * 4);
+                            cp_async16_cg(&sm.in_u[cc][slot * 32 + part * 4], gin_u + (col + 1) * H + row0 + part * 4);
                         if (col >= 0 && col < W) {
-                            cp_async16_cg(&sm.in_v[slot][cc][part * 4], gin_v + col * H + row0 + part * 4);
-                            if (!first_pass) cp_async16_cg(&sm.in_p[slot][cc][part * 4], gin_p + col * H + row0 + part * 4);
-                            cp_async4(&sm.in_f[slot][cc][part * 4], P.flags + col * H + row0 + part * 4);  // static data: L1 is fine
+                            cp_async16_cg(&sm.in_v[cc][slot * 32 + part * 4], gin_v + col * H + row0 + part * 4);
+                            if (!first_pass) cp_async16_cg(&sm.in_p[cc][slot * 32 + part * 4], gin_p + col * H + row0 + part * 4);
+                            cp_async4(&sm.in_f[cc][slot * 32 + part * 4], P.flags + col * H + row0 + part * 4);  // static data: L1 is fine
                         }
                     }
                 }
@@ -177,14 +178,23 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             };
 
             const int n_blk_needed = ((T - 1) >> 5) + 1;  // blocks the compute warps will wait for
+            TFS_TR_DECL
             load_block(0);
+            TFS_TR(0)
             for (int j = 0; j < n_int; ++j) {
                 load_records(j);
+                TFS_TR(1)
                 if ((j * G) % 32 == 0) {
                     const int n = (j * G) / 32 + 1;  // one block ahead of the compute warps
                     if (n < n_blk_needed) load_block(n);
+                    TFS_TR(2)
                 }
             }
+#ifdef TFS_SYS_TRACE
+            if (lane == 0 && P.trace) {
+                for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[(NW * 8 + i)], (unsigned long long)tr_acc[i]);
+            }
+#endif
         } else if (is_storer) {
             // ===================================== STORER ===========================================
             float *__restrict__ gout_u = P.buf[(tb + 1) & 1][0];
@@ -206,20 +216,25 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                         const long long col = q0 + cc - (KB - 1);
                         if (col >= 0 && col < W) {
                             const long long idx = col * H + row0 + part * 4;
-                            *reinterpret_cast<float4 *>(gout_u + idx) = *reinterpret_cast<const float4 *>(&sm.out_u[slot][cc][part * 4]);
-                            *reinterpret_cast<float4 *>(gout_v + idx) = *reinterpret_cast<const float4 *>(&sm.out_v[slot][cc][part * 4]);
-                            *reinterpret_cast<float4 *>(gout_p + idx) = *reinterpret_cast<const float4 *>(&sm.out_p[slot][cc][part * 4]);
+                            *reinterpret_cast<float4 *>(gout_u + idx) = *reinterpret_cast<const float4 *>(&sm.out_u[cc][slot * 32 + part * 4]);
+                            *reinterpret_cast<float4 *>(gout_v + idx) = *reinterpret_cast<const float4 *>(&sm.out_v[cc][slot * 32 + part * 4]);
+                            *reinterpret_cast<float4 *>(gout_p + idx) = *reinterpret_cast<const float4 *>(&sm.out_p[cc][slot * 32 + part * 4]);
                         }
                     }
                 }
             };
+            TFS_TR_DECL
             for (int j = 0; j < n_int; ++j) {
+                TFS_TR(0)
                 mbar_wait(&sm.rec_written[j % NPH], (j / NPH) & 1);  // steps < (j+1)*G retired by every k-group
+                TFS_TR(1)
                 const int t_done = min((j + 1) * G, T) - 1;
                 int m_first = m_next;
                 while (m_next <= m_last && done_step(m_next) <= t_done) { store_block(m_next); ++m_next; }
                 __syncwarp();
+                TFS_TR(2)
                 fence_gpu();  // release: block stores above + the records the compute warps wrote
+                TFS_TR(3)
                 if (lane == 0) {
                     int recs = t_done - 32 + 1;
                     recs = recs < 0 ? 0 : (recs > P.n_rec ? P.n_rec : recs);
@@ -233,6 +248,11 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     mbar_arrive(&sm.pub_done[j % NPH]);
                 }
             }
+#ifdef TFS_SYS_TRACE
+            if (lane == 0 && P.trace) {
+                for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[((NW + 1) * 8 + i)], (unsigned long long)tr_acc[i]);
+            }
+#endif
         } else {
             // ================================== compute warps =========================================
             const bool grav = first_pass && P.apply_gravity;
@@ -247,24 +267,30 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
 
             // k = 0 operands of step tau: u[q+1, rho], p[q, rho], flags[q, rho], v[q, rho+1], flags[q, rho+1]
-            // with rho = tau - lane - 1, read from the block ring (k-group 0 only)
+            // with rho = tau - lane - 1, read from the row rings (k-group 0 only).  rr / rr1 are this
+            // lane's ring positions of rho / rho + 1 and advance by one per step.
+            constexpr int RIN = 32 * NS_IN, ROUT = 32 * NS_OUT;
+            const int Hi = (int)H;
+            int rr = ((-lane - 1) % RIN + RIN) % RIN;      // rho at tau = 0
+            int rr1 = (rr + 1 == RIN) ? 0 : rr + 1;
             struct K0 { float su, sv, sp; unsigned f0, f1; };
-            auto load_k0 = [&](int tau) -> K0 {
-                const int rho = tau - lane - 1, rho1 = rho + 1;
-                const int blk = rho < 0 ? 0 : (rho >> 5), blk1 = rho1 < 0 ? 0 : (rho1 >> 5);
-                const int s0 = blk % NS_IN, s1 = blk1 % NS_IN;
+            auto load_k0 = [&]() -> K0 {  // operands of the step whose rho sits at rr
                 K0 o;
-                o.su = sm.in_u[s0][lane][rho & 31];
-                o.sp = sm.in_p[s0][lane][rho & 31];
-                o.f0 = sm.in_f[s0][lane][rho & 31];
-                o.sv = sm.in_v[s1][lane][rho1 & 31];
-                o.f1 = sm.in_f[s1][lane][rho1 & 31];
+                o.su = sm.in_u[lane][rr];
+                o.sp = sm.in_p[lane][rr];
+                o.f0 = sm.in_f[lane][rr];
+                o.sv = sm.in_v[lane][rr1];
+                o.f1 = sm.in_f[lane][rr1];
                 return o;
             };
+            auto advance_ring = [&]() {
+                rr = rr1;
+                rr1 = (rr1 + 1 == RIN) ? 0 : rr1 + 1;
+            };
             auto apply_k0 = [&](int tau, const K0 &o) {
-                const long long row = (long long)tau - lane - 1;
-                const bool row_ok = row >= 0 && row < H;
-                const bool rowp_ok = row + 1 >= 0 && row + 1 < H;
+                const int row = tau - lane - 1;
+                const bool row_ok = (unsigned)row < (unsigned)Hi;
+                const bool rowp_ok = (unsigned)(row + 1) < (unsigned)Hi;
                 const unsigned f0 = (col_ok && row_ok) ? o.f0 : 0u;
                 const unsigned f1 = (col_ok && rowp_ok) ? o.f1 : 0u;
                 uRo[0] = (colp_ok && row_ok) ? o.su : 0.0f;
@@ -274,44 +300,70 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 pin[0] = (!first_pass && col_ok && row_ok) ? o.sp : 0.0f;
                 fl = (fl & ~0xFu) | (f0 & 15u);
             };
-            // the first use of input block n: wait for it, and release block n-2 (its rows are behind lane 31)
-            auto acquire_in_block = [&](int n) {
-                mbar_wait(&sm.in_full[n % NS_IN], (n / NS_IN) & 1);
-                if (n >= 2) {
+            // input blocks: block n is first touched (by lane 0, row rho+1 = 32n) when preparing step 32n;
+            // block n-2 is then behind lane 31 and goes back to the loader
+            int in_slot = 0, in_par = 0, in_n = 0;         // next block to acquire
+            int rel_slot = 0;                              // slot of block in_n - 2
+            auto acquire_in_block = [&]() {
+                mbar_wait(&sm.in_full[in_slot], in_par);
+                if (in_n >= 2) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.in_empty[(n - 2) % NS_IN]);
+                    if (lane == 0) mbar_arrive(&sm.in_empty[rel_slot]);
+                    rel_slot = (rel_slot + 1 == NS_IN) ? 0 : rel_slot + 1;
                 }
+                ++in_n;
+                if (++in_slot == NS_IN) { in_slot = 0; in_par ^= 1; }
             };
             constexpr unsigned FULL = (KG == 8) ? 0xFFFFFFFFu : ((1u << (4 * KG)) - 1u);
             const bool group_active = (g + 1) * KG <= k_act;  // every iteration of this k-group runs in this pass
+            // record-interval bookkeeping (all k-groups) and output-ring bookkeeping (last k-group)
+            int rec_slot = 0, rec_par = 0;                  // slot / parity of the interval being consumed
+            int pub_slot = 0, pub_par = 0;                  // rec_written / pub_done slot of this interval
+            int j = 0;                                      // interval index
+            int ro = ((-lane - KB) % ROUT + ROUT) % ROUT;   // ring position of rho_out = t - lane - KB at t = 0
+            int out_m = NS_OUT, out_slot = 0, out_par = 0;  // next output block whose slot must be free again
+            const float4 *rec_base = &sm.rec[0][g][0][0];
+            constexpr int REC_SLOT_STRIDE = NW * G * KG;    // float4 per ring slot
 
             if (g == 0) {
-                acquire_in_block(0);
-                apply_k0(0, load_k0(0));
+                acquire_in_block();
+                apply_k0(0, load_k0());
+                advance_ring();
             }
-            for (int t = 0; t < T; ++t) {
-                const int j = t / G, sg = t % G;  // record interval, step inside it
+            TFS_TR_DECL
+            for (int t = 0, sg = 0; t < T; ++t) {
+                TFS_TR(0)
                 if (sg == 0) {
-                    mbar_wait(&sm.rec_full[j % NR], (j / NR) & 1);
+                    mbar_wait(&sm.rec_full[rec_slot], rec_par);
                     if (g == NW - 1) {
-                        // lane 0 is about to touch output block m = (t - KB) / 32 for the first time
-                        // (first touch of block m happens at step 32m + KB: wait if it falls in this interval)
-                        const int tt = t - KB;
-                        const int m = (tt + 31) >> 5;
-                        if (m >= NS_OUT && 32 * m - tt < G) mbar_wait(&sm.out_empty[m % NS_OUT], ((m / NS_OUT) & 1) ^ 1);
+                        // lane 0 first touches output block m at step 32m + KB: if that falls in this
+                        // interval and the slot was used before, the storer must have emptied it
+                        const int first = 32 * out_m + KB;
+                        if (first < t + G) {
+                            mbar_wait(&sm.out_empty[out_slot], out_par);
+                            ++out_m;
+                            if (++out_slot == NS_OUT) { out_slot = 0; out_par ^= 1; }
+                        }
                     }
                 }
+                TFS_TR(6)
                 const bool use_left = has_left && t < P.n_rec;
+                const bool patch = use_left && lane == 0;
                 // ---- early loads: left band's record (for lane 0) and next step's k = 0 operands
                 float4 lr[KG];
+                {
+                    const float4 *rp = rec_base + rec_slot * REC_SLOT_STRIDE + sg * KG;
 #pragma unroll
-                for (int kk = 0; kk < KG; ++kk) lr[kk] = sm.rec[j % NR][g][sg][kk];  // broadcast read
+                    for (int kk = 0; kk < KG; ++kk) lr[kk] = rp[kk];  // broadcast read
+                }
                 const bool have_next = (g == 0) && (t + 1 < T);
                 K0 nk0 = {0.f, 0.f, 0.f, 0u, 0u};
                 if (have_next) {
-                    if (((t + 1) & 31) == 0) acquire_in_block((t + 1) >> 5);
-                    nk0 = load_k0(t + 1);
+                    if (((t + 1) & 31) == 0) acquire_in_block();
+                    nk0 = load_k0();
+                    advance_ring();
                 }
+                TFS_TR(1)
                 // ---- KG independent cell updates ---------------------------------------------------
                 const unsigned fl_used = fl;
                 float a[KG], r[KG], cv[KG], d[KG], pp[KG];
@@ -340,7 +392,8 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                         cell_update4<2>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
                 }
                 // a = uCf (u of the cell after iteration k), r = uRp, cv = vCf, d = vTp, pp = pout
-                // ---- lane L-1's outputs ---------------------------------------------------------------
+                TFS_TR(2)
+                // ---- lane L-1's outputs ("lane -1" = lane 31 of the left band, zeros where there is none)
                 float n_uL[KG], s_v[KG], s_p[KG];
 #pragma unroll
                 for (int kk = 0; kk < KG; ++kk) {
@@ -349,26 +402,24 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     s_p[kk] = __shfl_up_sync(0xffffffffu, pp[kk], 1);
                 }
                 unsigned s_flv = __shfl_up_sync(0xffffffffu, fl_used, 1);
-                if (lane == 0) {  // "lane -1" is lane 31 of the left band (zeros where there is none)
 #pragma unroll
-                    for (int kk = 0; kk < KG; ++kk) {
-                        n_uL[kk] = use_left ? lr[kk].x : 0.0f;
-                        s_v[kk] = use_left ? lr[kk].y : 0.0f;
-                        s_p[kk] = use_left ? lr[kk].z : 0.0f;
-                    }
-                    s_flv = use_left ? __float_as_uint(lr[0].w) : 0u;
+                for (int kk = 0; kk < KG; ++kk) {
+                    n_uL[kk] = (lane == 0) ? (patch ? lr[kk].x : 0.0f) : n_uL[kk];
+                    s_v[kk] = (lane == 0) ? (patch ? lr[kk].y : 0.0f) : s_v[kk];
+                    s_p[kk] = (lane == 0) ? (patch ? lr[kk].z : 0.0f) : s_p[kk];
                 }
+                s_flv = (lane == 0) ? (patch ? __float_as_uint(lr[0].w) : 0u) : s_flv;
+                TFS_TR(3)
                 // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
                 sm.grp[t & 1][g][lane] =
                     make_float4(a[KG - 1], s_v[KG - 1], s_p[KG - 1], __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
                 if (g == NW - 1) {  // iteration KB-1 retired: final values of cell (q-(KB-1), t-lane-KB) -> output ring
-                    const int rho = t - lane - KB;
-                    if (rho >= 0) {
-                        const int slot = (rho >> 5) % NS_OUT;
-                        sm.out_u[slot][lane][rho & 31] = a[KG - 1];
-                        sm.out_v[slot][lane][rho & 31] = cv[KG - 1];
-                        sm.out_p[slot][lane][rho & 31] = pp[KG - 1];
+                    if (t - lane - KB >= 0) {
+                        sm.out_u[lane][ro] = a[KG - 1];
+                        sm.out_v[lane][ro] = cv[KG - 1];
+                        sm.out_p[lane][ro] = pp[KG - 1];
                     }
+                    ro = (ro + 1 == ROUT) ? 0 : ro + 1;
                 }
                 // ---- record of lane 31 for the same k-group of the next band (consumed at the end of ITS step t-32)
                 {
@@ -398,12 +449,20 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 if (sg == G - 1 || t == T - 1) {
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(&sm.rec_empty[j % NR]);
-                        if (j >= NPH) mbar_wait(&sm.pub_done[j % NPH], ((j / NPH) & 1) ^ 1);
-                        mbar_arrive(&sm.rec_written[j % NPH]);
+                        mbar_arrive(&sm.rec_empty[rec_slot]);
+                        if (j >= NPH) mbar_wait(&sm.pub_done[pub_slot], pub_par ^ 1);
+                        mbar_arrive(&sm.rec_written[pub_slot]);
                     }
+                    ++j;
+                    if (++rec_slot == NR) { rec_slot = 0; rec_par ^= 1; }
+                    if (++pub_slot == NPH) { pub_slot = 0; pub_par ^= 1; }
+                    sg = 0;
+                } else {
+                    ++sg;
                 }
+                TFS_TR(4)
                 bar_sync_imm<BAR_STEP, NCT>();
+                TFS_TR(5)
                 if (g > 0) {
                     const float4 gi = sm.grp[t & 1][g - 1][lane];
                     uRo[0] = gi.x;
@@ -415,6 +474,11 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     apply_k0(t + 1, nk0);
                 }
             }
+#ifdef TFS_SYS_TRACE
+            if (lane == 0 && P.trace) {
+                for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[(g * 8 + i)], (unsigned long long)tr_acc[i]);
+            }
+#endif
         }
     }
 }
@@ -454,6 +518,12 @@ struct Sys4Launch {
         P.buf[0][0] = *a.u; P.buf[0][1] = *a.v; P.buf[0][2] = *a.p;
         P.buf[1][0] = *a.u2; P.buf[1][1] = *a.v2; P.buf[1][2] = *a.p2;
         P.trace = nullptr;
+#ifdef TFS_SYS_TRACE
+        static long long *d_trace = nullptr;
+        if (!d_trace) cudaMalloc((void **)&d_trace, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), a.stream);
+        P.trace = d_trace;
+#endif
         const size_t rec_bytes = (size_t)2 * P.n_bands * NW * P.n_rec * KG * sizeof(float4);
         const size_t n_prog = (size_t)P.n_passes * P.n_bands;
         const size_t n_cnt = 2 * n_prog + 16;
@@ -512,6 +582,23 @@ struct Sys4Launch {
         kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
+#ifdef TFS_SYS_TRACE
+        {
+            long long h[64 * 8];
+            cudaStreamSynchronize(a.stream);
+            cudaMemcpy(h, P.trace, sizeof(h), cudaMemcpyDeviceToHost);
+            const double nsteps = (double)P.T * n_tasks, nint = (double)((P.T + G - 1) / G) * n_tasks;
+            const char *names[8] = {"loop", "early loads", "updates", "shuffles+patch", "stores+shift", "STEP bar issue", "rec_full wait", "-"};
+            for (int gq = 0; gq < NW; gq += (NW > 1 ? NW - 1 : 1)) {
+                fprintf(stderr, "[trace4] warp %d cycles/step:", gq);
+                for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], h[gq * 8 + i] / nsteps);
+                fprintf(stderr, "\n");
+            }
+            fprintf(stderr, "[trace4] loader cycles/interval: prologue=%.0f records=%.0f block=%.0f\n", h[NW * 8 + 0] / nint, h[NW * 8 + 1] / nint, h[NW * 8 + 2] / nint);
+            fprintf(stderr, "[trace4] storer cycles/interval: loop=%.0f wait_written=%.0f store=%.0f fence=%.0f\n", h[(NW + 1) * 8 + 0] / nint,
+                    h[(NW + 1) * 8 + 1] / nint, h[(NW + 1) * 8 + 2] / nint, h[(NW + 1) * 8 + 3] / nint);
+        }
+#endif
         if (P.n_passes & 1) {  // results are in set 1
             std::swap(*a.u, *a.u2);
             std::swap(*a.v, *a.v2);
