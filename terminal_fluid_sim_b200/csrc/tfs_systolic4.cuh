@@ -635,6 +635,10 @@ inline cudaError_t systolic_project_auto(const SystolicArgs &a, SystolicWorkspac
     TFS_SYS4_CASE(4, 3)
     TFS_SYS4_CASE(2, 5)
     TFS_SYS4_CASE(4, 8)
+    TFS_SYS4_CASE(8, 2)
+    TFS_SYS4_CASE(8, 4)
+    TFS_SYS4_CASE(6, 4)
+    TFS_SYS4_CASE(8, 1)
 #undef TFS_SYS4_CASE
     return systolic_project(a, ws, launched, msg);
 }
