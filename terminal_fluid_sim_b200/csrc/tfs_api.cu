@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -271,7 +272,13 @@ int phase_advect(tfs_sim *s, float dt) {
     if (rc) return rc;
     tfs::Grid g = s->grid();
     const long long W = (long long)s->W, H = (long long)s->H;
-    if (H % 4 == 0) {
+    const char *adv_env = getenv("TFS_ADVECT");  // tuning aid: "vec4" / "scalar" force the generic kernels
+    const bool fits32 = W * H < (1LL << 31) - (1LL << 20);
+    if (fits32 && !adv_env) {
+        constexpr int CPB = 8;
+        dim3 grid(blocks_for(H, 128), blocks_for(W, CPB));
+        tfs::k_advect32<CPB><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W, (int)H, dt, 1.0f);
+    } else if (H % 4 == 0 && !(adv_env && adv_env[0] == 's')) {
         tfs::k_advect<4><<<blocks_for(W * (H / 4), 256), 256, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2,
                                                                                s->s2, g, 0, W, dt);
     } else {

@@ -246,6 +246,98 @@ k_advect(const float *__restrict__ u, const float *__restrict__ v, const float *
 }
 
 // ---------------------------------------------------------------------------------------------
+// move_velocity, fast variant for single-GPU handles whose grid fits 32-bit indexing (N < 2^31):
+// one thread per cell, lanes along y, so every bilinear gather of a warp lands in one or two
+// 128-byte lines; all index arithmetic is 32-bit.  Same expression order as advect_cell above.
+// a + b and a - b issued as FFMA with a RUNTIME multiplier `one` (== 1.0f, a kernel argument, so
+// ptxas cannot fold it back into FADD): a*1 is exact, hence fma(a, 1, b) == RN(a + b) bit for bit.
+// On sm_100 FADD shares the ALU pipe with the integer / min-max / compare work that dominates this
+// kernel (ncu: ALU 60 % vs FMA 30 % busy); moving most adds to the FMA pipe balances the two.
+TFS_DEVINL float fadd_f(float a, float b, float one) { return __fmaf_rn(a, one, b); }
+TFS_DEVINL float fsub_f(float a, float b, float one) { return __fmaf_rn(b, -one, a); }
+
+template <int FT>
+TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, int W, int H, float Wf, float Hf,
+                                float one) {
+    const float dx = (FT == FT_U) ? 0.0f : 0.5f;   // simulator.rs:277-281
+    const float dy = (FT == FT_V) ? 0.0f : 0.5f;
+    x = fmaxf(fminf(x, Wf), 1.0f);                 // :271
+    y = fmaxf(fminf(y, Hf), 1.0f);                 // :272
+    const float xs = (FT == FT_U) ? x : fsub_f(x, dx, one), ys = (FT == FT_V) ? y : fsub_f(y, dy, one);  // x - 0.0 == x
+    const unsigned xl = min(__float2uint_rz(xs), (unsigned)(W - 1));   // :283 (xs >= 0.5: floor == trunc)
+    const float tx = fsub_f(xs, (float)xl, one);                       // :285
+    const unsigned yb = min(__float2uint_rz(ys), (unsigned)(H - 1));   // :287
+    const float ty = fsub_f(ys, (float)yb, one);                       // :289
+    const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);  // :291-292
+    // xr = min(xl+1, W-1), yt = min(yb+1, H-1) (:284, :288) as index offsets: +H / +1 unless clamped
+    const unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
+    const unsigned dyo = (yb < (unsigned)(H - 1)) ? 1u : 0u;
+    const unsigned i00 = xl * (unsigned)H + yb, i10 = i00 + dxo;
+    const float f00 = __ldg(f + i00), f10 = __ldg(f + i10);
+    const float f11 = __ldg(f + i10 + dyo), f01 = __ldg(f + i00 + dyo);
+    return fadd_f(fadd_f(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11), one),
+                  fmul(fmul(sx, ty), f01), one);   // :294-297
+}
+
+// blockDim.x threads along y (rows y0 .. y0+blockDim.x), CPB columns per block marched in +x so the
+// column i+1 values loaded for cell (i, j) are reused as "own" values of cell (i+1, j).
+template <int CPB>
+__global__ void __launch_bounds__(256)
+k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
+           const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
+           float *__restrict__ ns, int W, int H, float dt, float one) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.y * CPB;
+    if (j >= H) return;
+    const float Wf = (float)W, Hf = (float)H;
+    const float fj = (float)j, fjh = fadd(fj, 0.5f);
+    const int jm = j > 0 ? j - 1 : 0, jp = j < H - 1 ? j + 1 : j;   // clamped only for memory safety (border rows never use them)
+    unsigned idx = (unsigned)i0 * (unsigned)H + (unsigned)j;
+    // values of column i (own) and column i-1 (left)
+    float uC = u[idx], vC = v[idx], uB = u[idx - j + jm], vT = v[idx - j + jp];
+    float vL = 0.0f, vLT = 0.0f;
+    if (i0 > 0) { vL = v[idx - H]; vLT = v[idx - H - j + jp]; }
+#pragma unroll
+    for (int c = 0; c < CPB; ++c) {
+        const int i = i0 + c;
+        if (i >= W) break;
+        // column i+1 (right); clamped at the right border for memory safety only
+        const unsigned idr = (i + 1 < W) ? idx + (unsigned)H : idx;
+        const float uR = u[idr], uRB = u[idr - j + jm], vR = v[idr], vRT = v[idr - j + jp];
+        const float sC = s[idx];
+        const unsigned f = flags[idx];
+        float un = uC, vn = vC, sn = sC;
+        if (f & TFS_F_LIVE) {
+            const float fi = (float)i;
+            // u component (:207-213), avg_vertical (:245-255): ((((0+a)+b)+c)+d)*0.25
+            // (the leading "0 +" of Iterator::sum only affects the sign of a zero sum, which is then scaled
+            //  and subtracted from a coordinate >= 1: it cannot reach the result, so it is not issued)
+            const float avg_v = fmul(fadd_f(fadd(fadd(vL, vLT), vT), vC, one), 0.25f);
+            float xp = fsub_f(fi, fmul(uC, dt), one);
+            float yp = fsub_f(fjh, fmul(avg_v, dt), one);
+            un = sample_field32<FT_U>(u, xp, yp, W, H, Wf, Hf, one);
+            // v component (:216-224), avg_horizontal (:257-267)
+            const float avg_u = fmul(fadd_f(fadd(fadd(uB, uRB), uR), uC, one), 0.25f);
+            const float fih = fadd(fi, 0.5f);
+            xp = fsub_f(fih, fmul(avg_u, dt), one);
+            yp = fsub_f(fj, fmul(vC, dt), one);
+            vn = sample_field32<FT_V>(v, xp, yp, W, H, Wf, Hf, one);
+            // smoke (:227-237)
+            const float cv = fmul(fadd(vC, vT), 0.5f);
+            const float cu = fmul(fadd(uC, uR), 0.5f);
+            xp = fsub_f(fih, fmul(cu, dt), one);
+            yp = fsub_f(fjh, fmul(cv, dt), one);
+            sn = sample_field32<FT_S>(s, xp, yp, W, H, Wf, Hf, one);
+        }
+        nu[idx] = un; nv[idx] = vn; ns[idx] = sn;
+        // march: column i+1 becomes the own column, column i the left one
+        vL = vC; vLT = vT;
+        uC = uR; uB = uRB; vC = vR; vT = vRT;
+        idx = idr;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // reductions: warp shuffle -> one value per block -> second pass by one block.
 TFS_DEVINL float warp_min(float x) {
     for (int o = 16; o; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
