@@ -73,3 +73,21 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".rs")):
                     text = open(os.path.join(dirpath, f), errors="replace").read()
                     assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_cpp_mirror_compiles(lib, tmp_path):
+    """include/fluid_sim.hpp (the C++ host mirror of impl FluidSim) compiles and links against the .so."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "fluid_sim.hpp"\nint main() { tfs_options o; tfs_default_options(&o); return o.iterations == 50 ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)])
+    assert subprocess.call([str(exe)]) == 0
+
+
+def test_rust_bindings_cover_the_header():
+    """rust/tfs-sys (uncompiled: no Rust toolchain here) declares exactly the header's symbols."""
+    src = open(os.path.join(ROOT, "rust", "tfs-sys", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (tfs_[a-z_0-9]+)\(", src)))
+    assert declared == header_symbols()
