@@ -237,6 +237,10 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
     if (gravity_done) *gravity_done = false;
     const float pc = s->cfg.density / dt;  // :155 (inf for dt == 0, like the reference)
     const float omega = s->opt.omega;
+    if (s->opt.iterations == 0) {  // only `pressure_grid.fill(0.0)` remains (:154)
+        CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));
+        return TFS_OK;
+    }
     if (s->opt.mode == TFS_MODE_RED_BLACK) {
         CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));  // :154
         return project_redblack(s, omega, pc);
