@@ -259,7 +259,7 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
         a.stream = s->stream;
         const char *msg = nullptr;
         uint64_t launched = 0;
-        cudaError_t e = tfs::systolic_project_auto(a, s->sys, s->sys4, &launched, &msg);
+        cudaError_t e = tfs::systolic_project_auto(a, nullptr, s->sys, s->sys4, &launched, &msg);
         s->launches += launched;
         if (e != cudaSuccess)
             return fail(e == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "systolic projection: %s (%s)",

@@ -41,10 +41,45 @@ TFS_DEVINL void mbar_wait(unsigned long long *b, unsigned parity) {
         : "memory");
 }
 
+// x-slab placement of a handle (one process / GPU per slab).  A single-GPU handle is the slab
+// [0, W) with no neighbours.  Progress counters are 64-bit (seq << 32 | progress): `seq` grows by one
+// per projection, so counters never need a reset (a neighbour may write its mailbox entry before this
+// rank has even launched) and a stale value of an earlier projection always compares as "nothing yet".
+struct Sys4Slab {
+    long long xs0 = 0;     // global column of storage column 0
+    long long ncols = 0;   // stored columns
+    long long c_lo = 0;    // first owned column: final values of columns >= c_lo are stored locally ...
+    int b0 = 0;            // first global band of this rank
+    int nb_local = 0;      // number of bands this rank runs
+    int multi = 0;         // 1: neighbours exist -> system-scope fences
+    long long seq = 1;
+    float *peerL_buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // ... and columns <= c_lo also here
+    long long peerL_xs0 = 0;
+    float4 *rec_peerR[2] = {nullptr, nullptr};  // right rank's record slot 0 (per pass parity)
+    long long *bnd_prog_peerR = nullptr;        // right rank's bnd_prog mailbox (its index 0), row stride cnt_strideR
+    int cnt_strideR = 0;
+    long long *out_prog_peerL = nullptr;        // left rank's out_prog mailbox (its index nbL+1), row stride cnt_strideL
+    int cnt_strideL = 0;
+};
+
 struct Sys4Params {
     SysParams base;
-    const int2 *tasks;  // (pass, band) in issue order
+    const int2 *tasks;  // (pass, GLOBAL band) in issue order, local bands only
+    int n_tasks;
+    Sys4Slab slab;
+    long long *bnd_prog64;  // [n_passes][nb_local + 2]: index 0 = mailbox written by the left rank
+    long long *out_prog64;  // [n_passes][nb_local + 2]: index nb_local + 1 = mailbox written by the right rank
+    int cstride;            // row stride of the two counter arrays (>= nb_local + 2)
 };
+
+TFS_DEVINL long long ld_volatile64(const long long *p) { return *reinterpret_cast<const volatile long long *>(p); }
+TFS_DEVINL void st_volatile64(long long *p, long long v) { *reinterpret_cast<volatile long long *>(p) = v; }
+TFS_DEVINL void fence_sys() { asm volatile("fence.acq_rel.sys;\n" ::: "memory"); }
+TFS_DEVINL int prog_of(long long v, long long seq) {
+    const long long e = v >> 32;
+    return e < seq ? 0 : (e > seq ? 0x7fffffff : (int)(v & 0xffffffffLL));
+}
+TFS_DEVINL long long prog_make(long long seq, int x) { return (seq << 32) | (long long)(unsigned)x; }
 
 template <int KG, int NW, int G>
 struct Sys4Smem {
@@ -82,7 +117,9 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const bool is_loader = g == NW, is_storer = g == NW + 1;
     const long long W = P.W, H = P.H;
-    const int n_tasks = P.n_passes * P.n_bands;
+    const int n_tasks = P4.n_tasks;
+    const Sys4Slab &SL = P4.slab;
+    const int cstride = P4.cstride;
 
     for (;;) {
         __syncthreads();  // previous task fully retired (smem and mbarrier reuse)
@@ -98,7 +135,9 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
         const int ticket = sm.task;
         if (ticket >= n_tasks) break;
         const int2 tk = P4.tasks[ticket];
-        const int tb = tk.x, b = tk.y;
+        const int tb = tk.x, b = tk.y, lb = tk.y - SL.b0;  // pass, global band, local band
+        const int par = tb & 1;
+        const bool last_local = lb == SL.nb_local - 1;
         const int k_act = (tb == P.n_passes - 1) ? P.k_last : KB;
         const bool first_pass = tb == 0;
         const long long q0 = (long long)b * 32 - 1;  // skewed coordinate of lane 0
@@ -114,11 +153,16 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             const float *__restrict__ gin_u = P.buf[tb & 1][0];
             const float *__restrict__ gin_v = P.buf[tb & 1][1];
             const float *__restrict__ gin_p = P.buf[tb & 1][2];
-            const float4 *rec_in = P.bnd + ((size_t)(tb & 1) * P.n_bands + (b - 1)) * NW * rec_stride;
-            const int *left_prog = P.bnd_prog + (size_t)tb * P.n_bands + (b - 1);
-            const int *dep_out0 = P.out_prog + (size_t)(tb - 1) * P.n_bands + b;
-            const int *dep_out1 = P.out_prog + (size_t)(tb - 1) * P.n_bands + min(b + 1, P.n_bands - 1);
+            // record slot lb holds what the left band wrote (slot 0: the left rank's last band)
+            const float4 *rec_in = P.bnd + ((size_t)par * (SL.nb_local + 1) + lb) * NW * rec_stride;
+            const long long *left_prog = P4.bnd_prog64 + (size_t)tb * cstride + lb;
+            const long long *dep_out0 = P4.out_prog64 + (size_t)(tb - 1) * cstride + lb + 1;
+            const long long *dep_out1 = P4.out_prog64 + (size_t)(tb - 1) * cstride + ((b + 1 < P.n_bands) ? lb + 2 : lb + 1);
             int known_left = 0, known_rows = first_pass ? (int)H : 0;
+            const long long seq = SL.seq;
+            const float *bu = gin_u - SL.xs0 * H, *bv = gin_v - SL.xs0 * H, *bp = gin_p - SL.xs0 * H;  // global-column bases
+            const unsigned char *bf = P.flags - SL.xs0 * H;
+            const long long cs0 = SL.xs0, cs1 = SL.xs0 + SL.ncols;  // stored columns
 
             auto load_block = [&](int n) {
                 // rows [32n, 32n+32) of columns q0.. (u: q0+1..) -> slot n % NS_IN
@@ -129,10 +173,10 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 if (known_rows < need) {
                     do {
                         int k0 = 0;
-                        if (lane == 0) k0 = min(ld_volatile(dep_out0), ld_volatile(dep_out1));
+                        if (lane == 0) k0 = min(prog_of(ld_volatile64(dep_out0), seq), prog_of(ld_volatile64(dep_out1), seq));
                         known_rows = __shfl_sync(0xffffffffu, k0, 0);
                     } while (known_rows < need);
-                    fence_gpu();  // acquire
+                    if (SL.multi) fence_sys(); else fence_gpu();  // acquire
                 }
                 if (n < n_blk_in) {
                     const long long row0 = 32LL * n;
@@ -141,12 +185,12 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     for (int it = 0; it < 8; ++it) {
                         const int cc = it * 4 + (lane >> 3);
                         const long long col = q0 + cc;
-                        if (col + 1 >= 0 && col + 1 < W)
-                            cp_async16_cg(&sm.in_u[cc][slot * 32 + part * 4], gin_u + (col + 1) * H + row0 + part * 4);
-                        if (col >= 0 && col < W) {
-                            cp_async16_cg(&sm.in_v[cc][slot * 32 + part * 4], gin_v + col * H + row0 + part * 4);
-                            if (!first_pass) cp_async16_cg(&sm.in_p[cc][slot * 32 + part * 4], gin_p + col * H + row0 + part * 4);
-                            cp_async4(&sm.in_f[cc][slot * 32 + part * 4], P.flags + col * H + row0 + part * 4);  // static data: L1 is fine
+                        if (col + 1 >= 0 && col + 1 < W && col + 1 >= cs0 && col + 1 < cs1)
+                            cp_async16_cg(&sm.in_u[cc][slot * 32 + part * 4], bu + (col + 1) * H + row0 + part * 4);
+                        if (col >= 0 && col < W && col >= cs0 && col < cs1) {
+                            cp_async16_cg(&sm.in_v[cc][slot * 32 + part * 4], bv + col * H + row0 + part * 4);
+                            if (!first_pass) cp_async16_cg(&sm.in_p[cc][slot * 32 + part * 4], bp + col * H + row0 + part * 4);
+                            cp_async4(&sm.in_f[cc][slot * 32 + part * 4], bf + col * H + row0 + part * 4);  // static data: L1 is fine
                         }
                     }
                 }
@@ -161,10 +205,10 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     if (known_left < need) {
                         do {
                             int k0 = 0;
-                            if (lane == 0) k0 = ld_volatile(left_prog);
+                            if (lane == 0) k0 = prog_of(ld_volatile64(left_prog), seq);
                             known_left = __shfl_sync(0xffffffffu, k0, 0);
                         } while (known_left < need);
-                        fence_gpu();  // acquire
+                        if (SL.multi) fence_sys(); else fence_gpu();  // acquire
                     }
                     float4 *dst = &sm.rec[slot][0][0][0];
                     for (int e = lane; e < NW * G * KG; e += 32) {
@@ -200,8 +244,20 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             float *__restrict__ gout_u = P.buf[(tb + 1) & 1][0];
             float *__restrict__ gout_v = P.buf[(tb + 1) & 1][1];
             float *__restrict__ gout_p = P.buf[(tb + 1) & 1][2];
-            int *my_prog = P.bnd_prog + (size_t)tb * P.n_bands + b;
-            int *my_out_prog = P.out_prog + (size_t)tb * P.n_bands + b;
+            long long *my_prog = P4.bnd_prog64 + (size_t)tb * cstride + lb + 1;
+            long long *my_out_prog = P4.out_prog64 + (size_t)tb * cstride + lb + 1;
+            // boundary bands also publish into the neighbour rank's mailboxes
+            long long *peer_prog = (last_local && SL.bnd_prog_peerR) ? SL.bnd_prog_peerR + (size_t)tb * SL.cnt_strideR : nullptr;
+            long long *peer_out_prog = (lb == 0 && SL.out_prog_peerL) ? SL.out_prog_peerL + (size_t)tb * SL.cnt_strideL : nullptr;
+            const long long seq = SL.seq;
+            float *lu = gout_u - SL.xs0 * H, *lv = gout_v - SL.xs0 * H, *lp = gout_p - SL.xs0 * H;  // global-column bases
+            float *pu = nullptr, *pv = nullptr, *pp_ = nullptr;  // the left rank's copies (columns <= c_lo)
+            if (lb == 0 && SL.peerL_buf[(tb + 1) & 1][0]) {
+                pu = SL.peerL_buf[(tb + 1) & 1][0] - SL.peerL_xs0 * H;
+                pv = SL.peerL_buf[(tb + 1) & 1][1] - SL.peerL_xs0 * H;
+                pp_ = SL.peerL_buf[(tb + 1) & 1][2] - SL.peerL_xs0 * H;
+            }
+            const long long c_lo = SL.c_lo;
             int m_next = 0, rows_done = 0;
             // block m (rows [32m, 32m+32)) is complete once lane 31 retired its last row
             auto done_step = [&](int m) { return min(32 * m + 62 + KB, T - 1); };
@@ -216,9 +272,19 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                         const long long col = q0 + cc - (KB - 1);
                         if (col >= 0 && col < W) {
                             const long long idx = col * H + row0 + part * 4;
-                            *reinterpret_cast<float4 *>(gout_u + idx) = *reinterpret_cast<const float4 *>(&sm.out_u[cc][slot * 32 + part * 4]);
-                            *reinterpret_cast<float4 *>(gout_v + idx) = *reinterpret_cast<const float4 *>(&sm.out_v[cc][slot * 32 + part * 4]);
-                            *reinterpret_cast<float4 *>(gout_p + idx) = *reinterpret_cast<const float4 *>(&sm.out_p[cc][slot * 32 + part * 4]);
+                            const float4 vu = *reinterpret_cast<const float4 *>(&sm.out_u[cc][slot * 32 + part * 4]);
+                            const float4 vv = *reinterpret_cast<const float4 *>(&sm.out_v[cc][slot * 32 + part * 4]);
+                            const float4 vp = *reinterpret_cast<const float4 *>(&sm.out_p[cc][slot * 32 + part * 4]);
+                            if (col >= c_lo) {
+                                *reinterpret_cast<float4 *>(lu + idx) = vu;
+                                *reinterpret_cast<float4 *>(lv + idx) = vv;
+                                *reinterpret_cast<float4 *>(lp + idx) = vp;
+                            }
+                            if (pu && col <= c_lo) {  // owned by (or the first halo column of) the left rank
+                                *reinterpret_cast<float4 *>(pu + idx) = vu;
+                                *reinterpret_cast<float4 *>(pv + idx) = vv;
+                                *reinterpret_cast<float4 *>(pp_ + idx) = vp;
+                            }
                         }
                     }
                 }
@@ -233,16 +299,18 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 while (m_next <= m_last && done_step(m_next) <= t_done) { store_block(m_next); ++m_next; }
                 __syncwarp();
                 TFS_TR(2)
-                fence_gpu();  // release: block stores above + the records the compute warps wrote
+                if (SL.multi) fence_sys(); else fence_gpu();  // release: block stores above + the records the compute warps wrote
                 TFS_TR(3)
                 if (lane == 0) {
                     int recs = t_done - 32 + 1;
                     recs = recs < 0 ? 0 : (recs > P.n_rec ? P.n_rec : recs);
                     if (j == n_int - 1) recs = P.n_rec;
-                    st_volatile(my_prog, recs);
+                    st_volatile64(my_prog, prog_make(seq, recs));
+                    if (peer_prog) st_volatile64(peer_prog, prog_make(seq, recs));
                     if (m_next != m_first) {
                         rows_done = min(32 * m_next, (int)H);
-                        st_volatile(my_out_prog, rows_done);
+                        st_volatile64(my_out_prog, prog_make(seq, rows_done));
+                        if (peer_out_prog) st_volatile64(peer_out_prog, prog_make(seq, rows_done));
                     }
                     for (int m = m_first; m < m_next; ++m) mbar_arrive(&sm.out_empty[m % NS_OUT]);
                     mbar_arrive(&sm.pub_done[j % NPH]);
@@ -257,7 +325,10 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             // ================================== compute warps =========================================
             const bool grav = first_pass && P.apply_gravity;
             const long long q = q0 + lane;
-            float4 *rec_out = P.bnd + (((size_t)(tb & 1) * P.n_bands + b) * NW + g) * rec_stride;
+            // records go to slot lb + 1, or straight into slot 0 of the right rank for the last local band
+            float4 *rec_out = (last_local && SL.rec_peerR[par])
+                                  ? SL.rec_peerR[par] + (size_t)g * rec_stride
+                                  : P.bnd + (((size_t)par * (SL.nb_local + 1) + lb + 1) * NW + g) * rec_stride;
             const bool col_ok = q >= 0 && q < W;
             const bool colp_ok = q + 1 >= 0 && q + 1 < W;
 
@@ -485,18 +556,39 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
 
 // ---- host side ------------------------------------------------------------------------------------
 
+// Everything a slab handle provides from its arena (tfs_api.cu); nullptr in SystolicArgs = single GPU.
+struct Sys4External {
+    float4 *bnd = nullptr;          // record slots
+    size_t bnd_cap_f4 = 0;          // capacity in float4
+    long long *cnt = nullptr;       // [bnd_prog: max_passes*cstride][out_prog: max_passes*cstride]
+    int *ticket = nullptr;
+    int max_passes = 0, cstride = 0;
+    long long xs0 = 0, ncols = 0, c_lo = 0;
+    int b0 = 0, b0_next = -1;       // first band of this rank / of the right rank (-1: this is the last rank)
+    long long seq = 1;
+    // left neighbour (all null / 0 if none)
+    float *peerL_buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    long long peerL_xs0 = 0;
+    long long *peerL_cnt = nullptr; int peerL_cstride = 0, peerL_b0 = 0, peerL_max_passes = 0;
+    // right neighbour
+    float4 *peerR_bnd = nullptr;
+    long long *peerR_cnt = nullptr; int peerR_cstride = 0, peerR_b0 = 0, peerR_b0_next = -1;
+};
+
 struct Systolic4Workspace {
     int2 *d_tasks = nullptr;
+    int2 *h_tasks = nullptr;  // pinned, so the upload never blocks the host
     size_t n_tasks_cap = 0;
     long long key_W = -1, key_H = -1;
-    int key_passes = -1, key_bands = -1;
+    int key_passes = -1, key_bands = -1, key_b0 = -1, key_nbl = -1, key_kb = -1;
+    long long seq = 0;
 };
 
 template <int KG, int NW, int G>
 struct Sys4Launch {
     static constexpr int KB = KG * NW;
-    static cudaError_t run(const SystolicArgs &a, SystolicWorkspace &ws, Systolic4Workspace &ws4, uint64_t *launched,
-                           const char **msg) {
+    static cudaError_t run(const SystolicArgs &a, const Sys4External *ext, SystolicWorkspace &ws, Systolic4Workspace &ws4,
+                           uint64_t *launched, const char **msg) {
         cudaError_t e;
         int dev = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -506,10 +598,11 @@ struct Sys4Launch {
         const int K = a.iterations;
         Sys4Params P4{};
         SysParams &P = P4.base;
+        Sys4Slab &SL = P4.slab;
         P.W = a.W; P.H = a.H; P.ncells = a.W * a.H;
         P.n_passes = (K + KB - 1) / KB;
         P.k_last = K - (P.n_passes - 1) * KB;
-        P.n_bands = (int)((a.W + KB + 31) / 32);
+        P.n_bands = (int)((a.W + KB + 31) / 32);  // global
         P.T = (int)a.H + 32 + KB;
         P.n_rec = (int)a.H + KB;
         P.apply_gravity = a.fuse_gravity ? 1 : 0;
@@ -518,53 +611,87 @@ struct Sys4Launch {
         P.buf[0][0] = *a.u; P.buf[0][1] = *a.v; P.buf[0][2] = *a.p;
         P.buf[1][0] = *a.u2; P.buf[1][1] = *a.v2; P.buf[1][2] = *a.p2;
         P.trace = nullptr;
-#ifdef TFS_SYS_TRACE
-        static long long *d_trace = nullptr;
-        if (!d_trace) cudaMalloc((void **)&d_trace, 64 * 8 * sizeof(long long));
-        cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), a.stream);
-        P.trace = d_trace;
-#endif
-        const size_t rec_bytes = (size_t)2 * P.n_bands * NW * P.n_rec * KG * sizeof(float4);
-        const size_t n_prog = (size_t)P.n_passes * P.n_bands;
-        const size_t n_cnt = 2 * n_prog + 16;
-        const size_t need = rec_bytes + n_cnt * sizeof(int);
-        if (ws.bytes < need) {
-            if (ws.buf) cudaFree(ws.buf);
-            ws.buf = nullptr;
-            ws.bytes = 0;
-            if ((e = cudaMalloc(&ws.buf, need)) != cudaSuccess) { *msg = "workspace allocation"; return e; }
-            ws.bytes = need;
+        const size_t band_stride = (size_t)NW * P.n_rec * KG;  // float4 per record slot
+        if (!ext) {
+            SL.xs0 = 0; SL.ncols = a.W; SL.c_lo = 0; SL.b0 = 0; SL.nb_local = P.n_bands; SL.multi = 0;
+            SL.seq = ++ws4.seq;
+            P4.cstride = SL.nb_local + 2;
+            const size_t rec_bytes = (size_t)2 * (SL.nb_local + 1) * band_stride * sizeof(float4);
+            const size_t n_cnt = (size_t)2 * P.n_passes * P4.cstride;
+            const size_t need = rec_bytes + n_cnt * sizeof(long long) + 64;
+            if (ws.bytes < need) {
+                if (ws.buf) cudaFree(ws.buf);
+                ws.buf = nullptr;
+                ws.bytes = 0;
+                if ((e = cudaMalloc(&ws.buf, need)) != cudaSuccess) { *msg = "workspace allocation"; return e; }
+                if ((e = cudaMemsetAsync(ws.buf, 0, need, a.stream)) != cudaSuccess) return e;  // counters start below any seq
+                ws.bytes = need;
+            }
+            P.bnd = reinterpret_cast<float4 *>(ws.buf);
+            P4.bnd_prog64 = reinterpret_cast<long long *>(reinterpret_cast<char *>(ws.buf) + rec_bytes);
+            P4.out_prog64 = P4.bnd_prog64 + (size_t)P.n_passes * P4.cstride;
+            P.ticket = reinterpret_cast<int *>(P4.out_prog64 + (size_t)P.n_passes * P4.cstride);
+        } else {
+            SL.xs0 = ext->xs0; SL.ncols = ext->ncols; SL.c_lo = ext->c_lo; SL.b0 = ext->b0;
+            SL.nb_local = (ext->b0_next >= 0 ? ext->b0_next : P.n_bands) - ext->b0;
+            SL.multi = 1;
+            SL.seq = ext->seq;
+            if (SL.nb_local < 1) { *msg = "a slab must own at least one band"; return cudaErrorInvalidValue; }
+            if (P.n_passes > ext->max_passes || SL.nb_local + 2 > ext->cstride ||
+                (size_t)2 * (SL.nb_local + 1) * band_stride > ext->bnd_cap_f4) {
+                *msg = "slab workspace too small for this iteration count";
+                return cudaErrorInvalidValue;
+            }
+            P4.cstride = ext->cstride;
+            P.bnd = ext->bnd;
+            P4.bnd_prog64 = ext->cnt;
+            P4.out_prog64 = ext->cnt + (size_t)ext->max_passes * ext->cstride;
+            P.ticket = ext->ticket;
+            for (int i = 0; i < 2; ++i)
+                for (int f = 0; f < 3; ++f) SL.peerL_buf[i][f] = ext->peerL_buf[i][f];
+            SL.peerL_xs0 = ext->peerL_xs0;
+            if (ext->peerL_cnt) {  // the left rank's out_prog mailbox: its index nbL + 1
+                const int nbL = ext->b0 - ext->peerL_b0;
+                SL.out_prog_peerL = ext->peerL_cnt + (size_t)ext->peerL_max_passes * ext->peerL_cstride + (nbL + 1);
+                SL.cnt_strideL = ext->peerL_cstride;
+            }
+            if (ext->peerR_bnd) {
+                const int nbR = (ext->peerR_b0_next >= 0 ? ext->peerR_b0_next : P.n_bands) - ext->peerR_b0;
+                SL.rec_peerR[0] = ext->peerR_bnd;
+                SL.rec_peerR[1] = ext->peerR_bnd + (size_t)(nbR + 1) * band_stride;
+                SL.bnd_prog_peerR = ext->peerR_cnt;  // its index 0
+                SL.cnt_strideR = ext->peerR_cstride;
+            }
         }
-        P.bnd = reinterpret_cast<float4 *>(ws.buf);
-        int *cnt = reinterpret_cast<int *>(reinterpret_cast<char *>(ws.buf) + rec_bytes);
-        P.bnd_prog = cnt;
-        P.out_prog = cnt + n_prog;
-        P.ticket = cnt + 2 * n_prog;
-        if ((e = cudaMemsetAsync(cnt, 0, n_cnt * sizeof(int), a.stream)) != cudaSuccess) return e;
-        // task list in "start time" order: a band trails its left neighbour by ~lag_b steps and the
-        // same band of the previous pass by ~lag_t steps; every dependency has a strictly smaller key.
-        const long long n_tasks = (long long)P.n_passes * P.n_bands;
-        if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands) {
+        if ((e = cudaMemsetAsync(P.ticket, 0, sizeof(int), a.stream)) != cudaSuccess) return e;
+        // task list (local bands) in "start time" order: a band trails its left neighbour by ~lag_b steps
+        // and the same band of the previous pass by ~lag_t steps; every dependency has a strictly smaller
+        // key, on this rank and on its neighbours alike.
+        const long long n_tasks = (long long)P.n_passes * SL.nb_local;
+        if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands ||
+            ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB) {
+            if (ws4.n_tasks_cap < (size_t)n_tasks) {
+                if (ws4.d_tasks) cudaFree(ws4.d_tasks);
+                if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
+                ws4.d_tasks = nullptr; ws4.h_tasks = nullptr; ws4.n_tasks_cap = 0;
+                if ((e = cudaMalloc((void **)&ws4.d_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
+                if ((e = cudaMallocHost((void **)&ws4.h_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
+                ws4.n_tasks_cap = (size_t)n_tasks;
+            }
             const int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
             std::vector<std::pair<long long, int2>> v;
             v.reserve((size_t)n_tasks);
             for (int tb = 0; tb < P.n_passes; ++tb)
-                for (int b = 0; b < P.n_bands; ++b) v.push_back({(long long)b * lag_b + (long long)tb * lag_t, make_int2(tb, b)});
+                for (int b = SL.b0; b < SL.b0 + SL.nb_local; ++b)
+                    v.push_back({(long long)b * lag_b + (long long)tb * lag_t, make_int2(tb, b)});
             std::stable_sort(v.begin(), v.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
-            std::vector<int2> order((size_t)n_tasks);
-            for (size_t i = 0; i < v.size(); ++i) order[i] = v[i].second;
-            if (ws4.n_tasks_cap < (size_t)n_tasks) {
-                if (ws4.d_tasks) cudaFree(ws4.d_tasks);
-                ws4.d_tasks = nullptr;
-                ws4.n_tasks_cap = 0;
-                if ((e = cudaMalloc((void **)&ws4.d_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
-                ws4.n_tasks_cap = (size_t)n_tasks;
-            }
-            if ((e = cudaMemcpyAsync(ws4.d_tasks, order.data(), (size_t)n_tasks * sizeof(int2), cudaMemcpyHostToDevice, a.stream)) != cudaSuccess) return e;
-            if ((e = cudaStreamSynchronize(a.stream)) != cudaSuccess) return e;  // `order` is a local
+            for (size_t i = 0; i < v.size(); ++i) ws4.h_tasks[i] = v[i].second;
+            if ((e = cudaMemcpyAsync(ws4.d_tasks, ws4.h_tasks, (size_t)n_tasks * sizeof(int2), cudaMemcpyHostToDevice, a.stream)) != cudaSuccess) return e;
             ws4.key_W = a.W; ws4.key_H = a.H; ws4.key_passes = P.n_passes; ws4.key_bands = P.n_bands;
+            ws4.key_b0 = SL.b0; ws4.key_nbl = SL.nb_local; ws4.key_kb = KB;
         }
         P4.tasks = ws4.d_tasks;
+        P4.n_tasks = (int)n_tasks;
         auto kern = k_project_systolic4<KG, NW, G>;
         const size_t smem = sizeof(Sys4Smem<KG, NW, G>) + 128;
         static bool attr_set = false;
@@ -579,6 +706,12 @@ struct Sys4Launch {
         }
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
         const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
+#ifdef TFS_SYS_TRACE
+        static long long *d_trace = nullptr;
+        if (!d_trace) cudaMalloc((void **)&d_trace, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), a.stream);
+        P.trace = d_trace;
+#endif
         kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
@@ -610,36 +743,47 @@ struct Sys4Launch {
 
 inline void systolic4_release(Systolic4Workspace &ws4) {
     if (ws4.d_tasks) cudaFree(ws4.d_tasks);
+    if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
     ws4.d_tasks = nullptr;
+    ws4.h_tasks = nullptr;
     ws4.n_tasks_cap = 0;
     ws4.key_W = ws4.key_H = -1;
 }
 
-// H % 4 == 0: the block-ring kernel; otherwise the generic cp.async-4 kernel of tfs_systolic.cuh
-inline cudaError_t systolic_project_auto(const SystolicArgs &a, SystolicWorkspace &ws, Systolic4Workspace &ws4,
-                                         uint64_t *launched, const char **msg) {
+// The block-ring kernel needs H % 4 == 0 (16-byte column alignment); otherwise the generic cp.async-4
+// kernel of tfs_systolic.cuh runs (single GPU only).
+inline bool systolic4_usable(const SystolicArgs &a) {
     const char *force_v3 = getenv("TFS_SYS_V3");
-    if ((a.H % 4) != 0 || (force_v3 && atoi(force_v3))) return systolic_project(a, ws, launched, msg);
+    return (a.H % 4) == 0 && !(force_v3 && atoi(force_v3));
+}
+
+inline cudaError_t systolic_project_auto(const SystolicArgs &a, const Sys4External *ext, SystolicWorkspace &ws,
+                                         Systolic4Workspace &ws4, uint64_t *launched, const char **msg) {
+    if (!systolic4_usable(a)) {
+        if (ext) { *msg = "x-slab handles need H % 4 == 0"; return cudaErrorInvalidValue; }
+        return systolic_project(a, ws, launched, msg);
+    }
     const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
     const char *env_g = getenv("TFS_SYS_G");
     const int G_ = env_g ? atoi(env_g) : 8;
 #define TFS_SYS4_CASE(KG_, NW_)                                                                          \
     if (sh.kg == KG_ && sh.nw == NW_) {                                                                  \
-        if (G_ == 4) return Sys4Launch<KG_, NW_, 4>::run(a, ws, ws4, launched, msg);                     \
-        return Sys4Launch<KG_, NW_, 8>::run(a, ws, ws4, launched, msg);                                  \
+        if (G_ == 4) return Sys4Launch<KG_, NW_, 4>::run(a, ext, ws, ws4, launched, msg);                \
+        return Sys4Launch<KG_, NW_, 8>::run(a, ext, ws, ws4, launched, msg);                             \
     }
+    TFS_SYS4_CASE(6, 4)
+    TFS_SYS4_CASE(4, 8)
     TFS_SYS4_CASE(4, 4)
-    TFS_SYS4_CASE(2, 8)
-    TFS_SYS4_CASE(4, 2)
-    TFS_SYS4_CASE(2, 4)
     TFS_SYS4_CASE(4, 3)
     TFS_SYS4_CASE(2, 5)
-    TFS_SYS4_CASE(4, 8)
+    TFS_SYS4_CASE(4, 2)
+    TFS_SYS4_CASE(2, 8)
+    TFS_SYS4_CASE(2, 4)
     TFS_SYS4_CASE(8, 2)
     TFS_SYS4_CASE(8, 4)
-    TFS_SYS4_CASE(6, 4)
     TFS_SYS4_CASE(8, 1)
 #undef TFS_SYS4_CASE
+    if (ext) return Sys4Launch<4, 4, 8>::run(a, ext, ws, ws4, launched, msg);
     return systolic_project(a, ws, launched, msg);
 }
 
