@@ -153,12 +153,24 @@ int tfs_launch_count(const tfs_sim *sim, uint64_t *launches);
  * every f32 x and n in {1,2,3,4}; *mismatches must come back 0 */
 int tfs_selftest_division(int device, uint64_t *mismatches);
 
-/* ---- multi-GPU x-slabs (one handle per process per GPU); see DESIGN.md ---- */
-/* opaque blob (TFS_PEER_BLOB_BYTES) describing this handle's exported buffers */
+/* ---- multi-GPU x-slabs (one handle per GPU, normally one process each); see DESIGN.md section 6 ----
+ * A handle created with options.world > 1 owns the columns [c_lo, c_hi) of the global width x height
+ * grid (plus a few halo columns).  Every rank makes the same calls in the same order.  Edits
+ * (tfs_set_block, tfs_upload_blocks, tfs_write_field, scenes) always take GLOBAL coordinates / the
+ * GLOBAL array and each rank keeps its part; tfs_read_field returns the OWNED columns,
+ * tfs_read_view accepts windows inside the stored columns; tfs_pressure_minmax and
+ * tfs_divergence_linf report the rank's own share.  Neighbours exchange halo columns, the projection's
+ * band records and progress counters by direct peer stores (CUDA IPC across processes) - no
+ * collective; tfs_step never blocks the host. */
 #define TFS_PEER_BLOB_BYTES 512
+/* opaque, fixed-size description of this handle's device arena, to be handed to its neighbours */
 int tfs_peer_export(tfs_sim *sim, void *blob);
-/* attach the blobs of the left / right neighbour slab (NULL where there is none) */
+/* attach the blobs of the left / right neighbour slab (NULL exactly where there is none) */
 int tfs_peer_attach(tfs_sim *sim, const void *left_blob, const void *right_blob);
+/* the column range rank `rank` of `world` owns for a grid of `width` columns (host arithmetic only) */
+int tfs_slab_bounds(size_t width, int rank, int world, size_t *c_lo, size_t *c_hi);
+/* owned [c_lo, c_hi) and stored [stored_lo, stored_hi) columns of a handle (stored_* may be NULL) */
+int tfs_get_slab(const tfs_sim *sim, size_t *c_lo, size_t *c_hi, size_t *stored_lo, size_t *stored_hi);
 
 #ifdef __cplusplus
 }

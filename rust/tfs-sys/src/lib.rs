@@ -78,4 +78,6 @@ extern "C" {
     pub fn tfs_selftest_division(device: c_int, mismatches: *mut u64) -> c_int;
     pub fn tfs_peer_export(sim: *mut tfs_sim, blob: *mut c_void) -> c_int;
     pub fn tfs_peer_attach(sim: *mut tfs_sim, left_blob: *const c_void, right_blob: *const c_void) -> c_int;
+    pub fn tfs_slab_bounds(width: usize, rank: c_int, world: c_int, c_lo: *mut usize, c_hi: *mut usize) -> c_int;
+    pub fn tfs_get_slab(sim: *const tfs_sim, c_lo: *mut usize, c_hi: *mut usize, stored_lo: *mut usize, stored_hi: *mut usize) -> c_int;
 }

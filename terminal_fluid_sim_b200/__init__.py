@@ -4,7 +4,7 @@ libtfs_cuda.so (csrc/, C ABI in include/tfs.h); importing FluidSim without the b
 raises ImportError: there is no CPU fallback."""
 from .fluid_sim import (FIELD_FLAGS, FIELD_M, FIELD_P, FIELD_S, FIELD_U, FIELD_V, KERNEL_AUTO,  # noqa: F401
                         KERNEL_DIAGONAL, KERNEL_SYSTOLIC, MODE_RED_BLACK, MODE_WAVEFRONT_EXACT,
-                        FluidSim, PinnedBuffer, SimConfig, selftest_division)
+                        FluidSim, PinnedBuffer, SimConfig, SlabGroup, selftest_division, slab_bounds)
 from ._lib import TfsError  # noqa: F401
 
-__all__ = ["FluidSim", "SimConfig", "PinnedBuffer", "TfsError", "selftest_division"]
+__all__ = ["FluidSim", "SimConfig", "PinnedBuffer", "SlabGroup", "TfsError", "selftest_division", "slab_bounds"]

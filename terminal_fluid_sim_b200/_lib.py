@@ -20,6 +20,7 @@ SYMBOLS = [
     "tfs_scene_disc", "tfs_scene_lattice", "tfs_scene_random", "tfs_fill_random_velocity",
     "tfs_host_alloc", "tfs_host_free", "tfs_timer_begin", "tfs_timer_end", "tfs_set_profiling",
     "tfs_get_phase_ms", "tfs_launch_count", "tfs_selftest_division", "tfs_peer_export", "tfs_peer_attach",
+    "tfs_slab_bounds", "tfs_get_slab",
 ]
 
 
@@ -97,6 +98,8 @@ def load():
     L.tfs_selftest_division.argtypes = [i32, C.POINTER(u64)]
     L.tfs_peer_export.argtypes = [vp, vp]
     L.tfs_peer_attach.argtypes = [vp, vp, vp]
+    L.tfs_slab_bounds.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.tfs_get_slab.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     _lib = L
     return L
 

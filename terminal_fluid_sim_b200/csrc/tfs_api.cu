@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <new>
 #include <vector>
 
@@ -75,12 +76,93 @@ struct tfs_sim {
     double acc_ms[3] = {0, 0, 0};
     uint64_t acc_steps = 0;
     uint64_t launches = 0;
+    // ---- x-slab placement (world == 1: the slab is the whole grid) ----
+    int rank = 0, world = 1;
+    long long c_lo = 0, c_hi = 0;  // owned global columns [c_lo, c_hi)
+    long long xs0 = 0, ncols = 0;  // stored global columns [xs0, xs0 + ncols) (owned + halos)
+    int b0 = 0, b0_next = -1;      // first band of this rank / of the right rank (-1: last rank)
+    char *arena = nullptr;         // slab handles keep everything in ONE allocation (one IPC handle)
+    struct Layout {
+        size_t off_f32[8] = {0}, off_m = 0, off_flags = 0, off_sync = 0, off_cnt = 0, off_ticket = 0, off_bnd = 0, total = 0;
+        size_t bnd_cap_f4 = 0;
+        int cstride = 0, max_passes = 0;
+    } lay;
+    int phys[8] = {0, 1, 2, 3, 4, 5, 6, 7};  // logical u v p s u2 v2 p2 s2 -> physical array index
+    struct Peer {
+        bool present = false, ipc = false;
+        char *base = nullptr;
+        long long xs0 = 0, ncols = 0, c_lo = 0, c_hi = 0;
+        int b0 = 0, b0_next = -1;
+        Layout lay;
+    } peerL, peerR;
+    bool attached = false;
+    long long step_seq = 0;        // projections run so far (same on every rank)
+    int *d_oob = nullptr;          // device flag: an advection sample fell outside the stored columns
 
-    tfs::Grid grid() const { return tfs::Grid{(long long)W, (long long)H, 0, (long long)W}; }
-    long long n() const { return (long long)W * (long long)H; }
+    tfs::Grid grid() const { return tfs::Grid{(long long)W, (long long)H, xs0, ncols}; }
+    long long n() const { return ncols * (long long)H; }          // stored cells
+    long long gn() const { return (long long)W * (long long)H; }  // cells of the global grid
+    bool slab() const { return world > 1; }
 };
 
 namespace {
+
+constexpr long long kHalo = 8;        // halo columns kept on each side of a slab (advection reach + 1 for the projection)
+constexpr int kSlabMaxPasses = 64;    // passes a slab workspace is sized for
+constexpr unsigned kBlobMagic = 0x54465331u;  // "TFS1"
+
+struct SlabGeom { long long c_lo, c_hi, xs0, xs1; int b0, b0_next; };
+
+// Bands (32 values of the skewed coordinate, band b covering columns [32b-1, 32b+30] at k = 0) are split
+// evenly over the ranks; a rank owns the columns of its bands.  Pure host arithmetic (tfs_slab_bounds).
+SlabGeom slab_geom(long long W, int rank, int world) {
+    const long long nb0 = (W + 1 + 31) / 32;  // bands that contain real columns (-1 .. W-1)
+    auto bstart = [&](int r) { return (long long)r * nb0 / world; };
+    SlabGeom g;
+    g.b0 = (int)bstart(rank);
+    g.b0_next = rank == world - 1 ? -1 : (int)bstart(rank + 1);
+    g.c_lo = rank == 0 ? 0 : 32 * bstart(rank) - 1;
+    g.c_hi = rank == world - 1 ? W : 32 * bstart(rank + 1) - 1;
+    g.xs0 = std::max(0LL, g.c_lo - kHalo);
+    g.xs1 = std::min(W, g.c_hi + kHalo);
+    return g;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+tfs_sim::Layout slab_layout(long long W, long long H, long long ncols, int b0, int b0_next) {
+    tfs_sim::Layout L;
+    const size_t cells = (size_t)(ncols * H) + 64;
+    size_t off = 0;
+    for (int i = 0; i < 8; ++i) { L.off_f32[i] = off; off += align_up(cells * sizeof(float), 256); }
+    L.off_m = off; off += align_up(cells, 256);
+    L.off_flags = off; off += align_up(cells, 256);
+    L.off_sync = off; off += 256;
+    const int nb_max = (int)((b0_next >= 0 ? b0_next : (W + 32 + 31) / 32) - b0);  // KB <= 32
+    L.cstride = nb_max + 2;
+    L.max_passes = kSlabMaxPasses;
+    L.off_cnt = off; off += align_up((size_t)2 * L.max_passes * L.cstride * sizeof(long long), 256);
+    L.off_ticket = off; off += 256;
+    L.bnd_cap_f4 = (size_t)2 * (nb_max + 1) * 32 * (size_t)(H + 32);
+    L.off_bnd = off; off += align_up(L.bnd_cap_f4 * sizeof(float4), 256);
+    L.total = off;
+    return L;
+}
+
+// indices into the sync area (long long each); all are written by a NEIGHBOUR into this rank's memory
+enum { SYNC_PUSHA_FROM_L = 0, SYNC_PUSHA_FROM_R, SYNC_PUSHB_FROM_L, SYNC_PUSHB_FROM_R, SYNC_ADVDONE_FROM_L, SYNC_ADVDONE_FROM_R,
+       SYNC_PROJDONE_FROM_R };
+
+struct PeerBlob {
+    unsigned magic;
+    int rank, world, device;
+    long long W, H, xs0, ncols, c_lo, c_hi;
+    int b0, b0_next;
+    unsigned long long pid;
+    unsigned long long raw_ptr;
+    cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(PeerBlob) <= TFS_PEER_BLOB_BYTES, "blob too large");
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -89,7 +171,24 @@ int set_device(const tfs_sim *s) {
     return TFS_OK;
 }
 
+float *&logical(tfs_sim *s, int i) {
+    float **fp[] = {&s->u, &s->v, &s->p, &s->s, &s->u2, &s->v2, &s->p2, &s->s2};
+    return *fp[i];
+}
+float *peer_logical(const tfs_sim *s, const tfs_sim::Peer &p, int i) {
+    return reinterpret_cast<float *>(p.base + p.lay.off_f32[s->phys[i]]);
+}
+long long *sync_slot(char *base, const tfs_sim::Layout &L, int idx) { return reinterpret_cast<long long *>(base + L.off_sync) + idx; }
+
 void free_fields(tfs_sim *s) {
+    if (s->arena) {
+        cudaFree(s->arena);
+        s->arena = nullptr;
+        s->u = s->v = s->p = s->s = s->u2 = s->v2 = s->p2 = s->s2 = nullptr;
+        s->m = s->flags = nullptr;
+        s->cap = 0;
+        return;
+    }
     float **fp[] = {&s->u, &s->v, &s->p, &s->s, &s->u2, &s->v2, &s->p2, &s->s2};
     for (auto f : fp) {
         if (*f) cudaFree(*f);
@@ -104,6 +203,17 @@ void free_fields(tfs_sim *s) {
 // allocate all arrays for `cells` cells (+ one padding column worth so vector tails are safe)
 int alloc_fields(tfs_sim *s, size_t cells) {
     free_fields(s);
+    if (s->slab()) {
+        s->lay = slab_layout((long long)s->W, (long long)s->H, s->ncols, s->b0, s->b0_next);
+        CU(cudaMalloc((void **)&s->arena, s->lay.total));
+        // masks, flags, sync flags, counters and ticket start at zero (fields are filled by reset_fields)
+        CU(cudaMemsetAsync(s->arena + s->lay.off_m, 0, s->lay.off_bnd - s->lay.off_m, s->stream));
+        for (int i = 0; i < 8; ++i) { s->phys[i] = i; logical(s, i) = reinterpret_cast<float *>(s->arena + s->lay.off_f32[i]); }
+        s->m = reinterpret_cast<uint8_t *>(s->arena + s->lay.off_m);
+        s->flags = reinterpret_cast<uint8_t *>(s->arena + s->lay.off_flags);
+        s->cap = cells;
+        return TFS_OK;
+    }
     size_t padded = cells + 64;
     float **fp[] = {&s->u, &s->v, &s->p, &s->s, &s->u2, &s->v2, &s->p2, &s->s2};
     for (auto f : fp) CU(cudaMalloc((void **)f, padded * sizeof(float)));
@@ -124,7 +234,7 @@ size_t f32_as_usize(float x) {
 
 // set_horizontal_speed (simulator.rs:79-85) and set_smoke_pipe (:94-111) on the device copy
 int apply_wind_and_pipe(tfs_sim *s) {
-    const long long H = (long long)s->H, n = s->n();
+    const long long H = (long long)s->H, n = s->gn();  // ranges are GLOBAL flat indices; the fill kernels clip to the slab
     tfs::Grid g = s->grid();
     long long lo = H, hi = std::min(2 * H, n);
     if (hi > lo) {
@@ -162,7 +272,7 @@ int reset_fields(tfs_sim *s) {
 int refresh_flags(tfs_sim *s) {
     if (!s->flags_dirty) return TFS_OK;
     tfs::Grid g = s->grid();
-    tfs::k_cell_flags<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->flags, g, 0, (long long)s->W);
+    tfs::k_cell_flags<<<blocks_for(s->n(), 256), 256, 0, s->stream>>>(s->m, s->flags, g, 0, s->ncols);
     s->launches++;
     CU(cudaGetLastError());
     s->flags_dirty = false;
@@ -178,7 +288,6 @@ int check_options(const tfs_options *o) {
     NEED(o->temporal_block >= 0 && o->temporal_block <= tfs::kMaxTemporalBlock, TFS_ERR_INVALID_ARG,
          "options.temporal_block out of range");
     NEED(o->world >= 1 && o->rank >= 0 && o->rank < o->world, TFS_ERR_INVALID_ARG, "bad rank/world");
-    NEED(o->world == 1, TFS_ERR_INVALID_ARG, "multi-slab handles are not available in this build");
     return TFS_OK;
 }
 
@@ -259,7 +368,46 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
         a.stream = s->stream;
         const char *msg = nullptr;
         uint64_t launched = 0;
-        cudaError_t e = tfs::systolic_project_auto(a, nullptr, s->sys, s->sys4, &launched, &msg);
+        tfs::Sys4External ext{};
+        const tfs::Sys4External *extp = nullptr;
+        if (s->slab()) {
+            NEED(s->attached, TFS_ERR_COMM, "x-slab handle: call tfs_peer_attach before stepping");
+            ext.bnd = reinterpret_cast<float4 *>(s->arena + s->lay.off_bnd);
+            ext.bnd_cap_f4 = s->lay.bnd_cap_f4;
+            ext.cnt = reinterpret_cast<long long *>(s->arena + s->lay.off_cnt);
+            ext.ticket = reinterpret_cast<int *>(s->arena + s->lay.off_ticket);
+            ext.max_passes = s->lay.max_passes;
+            ext.cstride = s->lay.cstride;
+            ext.xs0 = s->xs0; ext.ncols = s->ncols; ext.c_lo = s->c_lo; ext.b0 = s->b0; ext.b0_next = s->b0_next;
+            ext.seq = s->step_seq;
+            if (s->peerL.present) {
+                // set 0 = logical (u, v, p), set 1 = logical (u2, v2, p2) -- the same mapping on every rank
+                for (int f = 0; f < 3; ++f) {
+                    ext.peerL_buf[0][f] = peer_logical(s, s->peerL, f);
+                    ext.peerL_buf[1][f] = peer_logical(s, s->peerL, 4 + f);
+                }
+                ext.peerL_xs0 = s->peerL.xs0;
+                ext.peerL_cnt = reinterpret_cast<long long *>(s->peerL.base + s->peerL.lay.off_cnt);
+                ext.peerL_cstride = s->peerL.lay.cstride;
+                ext.peerL_max_passes = s->peerL.lay.max_passes;
+                ext.peerL_b0 = s->peerL.b0;
+            }
+            if (s->peerR.present) {
+                ext.peerR_bnd = reinterpret_cast<float4 *>(s->peerR.base + s->peerR.lay.off_bnd);
+                ext.peerR_cnt = reinterpret_cast<long long *>(s->peerR.base + s->peerR.lay.off_cnt);
+                ext.peerR_cstride = s->peerR.lay.cstride;
+                ext.peerR_b0 = s->peerR.b0;
+                ext.peerR_b0_next = s->peerR.b0_next;
+            }
+            extp = &ext;
+        }
+        float *u_before = s->u;
+        cudaError_t e = tfs::systolic_project_auto(a, extp, s->sys, s->sys4, &launched, &msg);
+        if (e == cudaSuccess && s->u != u_before) {  // odd pass count: the ping-pong sets were swapped
+            std::swap(s->phys[0], s->phys[4]);
+            std::swap(s->phys[1], s->phys[5]);
+            std::swap(s->phys[2], s->phys[6]);
+        }
         s->launches += launched;
         if (e != cudaSuccess)
             return fail(e == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "systolic projection: %s (%s)",
@@ -278,7 +426,15 @@ int phase_advect(tfs_sim *s, float dt) {
     const long long W = (long long)s->W, H = (long long)s->H;
     const char *adv_env = getenv("TFS_ADVECT");  // tuning aid: "vec4" / "scalar" force the generic kernels
     const bool fits32 = W * H < (1LL << 31) - (1LL << 20);
-    if (fits32 && !adv_env) {
+    if (s->slab()) {
+        // owned columns only; pointers are rebased to global columns, halos supply the neighbours' cells
+        constexpr int CPB = 8;
+        const long long sh = s->xs0 * H;
+        dim3 grid(blocks_for(H, 128), blocks_for(s->c_hi - s->c_lo, CPB));
+        tfs::k_advect32<CPB, true><<<grid, 128, 0, s->stream>>>(s->u - sh, s->v - sh, s->s - sh, s->flags - sh, s->u2 - sh, s->v2 - sh,
+                                                                 s->s2 - sh, (int)W, (int)H, dt, 1.0f, (int)s->c_lo, (int)s->c_hi,
+                                                                 (unsigned)s->xs0, (unsigned)(s->xs0 + s->ncols - 1), s->d_oob);
+    } else if (fits32 && !adv_env) {
         constexpr int CPB = 8;
         dim3 grid(blocks_for(H, 128), blocks_for(W, CPB));
         tfs::k_advect32<CPB><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W, (int)H, dt, 1.0f);
@@ -294,6 +450,98 @@ int phase_advect(tfs_sim *s, float dt) {
     std::swap(s->u, s->u2);  // simulator.rs:240-242
     std::swap(s->v, s->v2);
     std::swap(s->s, s->s2);
+    std::swap(s->phys[0], s->phys[4]);
+    std::swap(s->phys[1], s->phys[5]);
+    std::swap(s->phys[3], s->phys[7]);
+    return TFS_OK;
+}
+
+// ---- x-slab halo exchange ------------------------------------------------------------------------
+// Copy `ncopy` owned boundary columns of the logical fields in `which` into the neighbours' halo
+// columns (peer stores over NVLink), then raise `flag_idx_*` in the neighbours' sync areas to `seq`.
+int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq) {
+    const long long H = (long long)s->H;
+    const long long n4 = kHalo * H / 4;
+    const unsigned gb = std::min<unsigned>(blocks_for(n4, 256), 148 * 4);
+    for (int side = 0; side < 2; ++side) {
+        tfs_sim::Peer &p = side == 0 ? s->peerL : s->peerR;
+        if (!p.present) continue;
+        // to the left rank: my first kHalo owned columns -> its right halo; to the right rank: my last kHalo -> its left halo
+        const long long col = side == 0 ? s->c_lo : s->c_hi - kHalo;
+        for (int i = 0; i < nwhich; ++i) {
+            const float *src = logical(s, which[i]) + (col - s->xs0) * H;
+            float *dst = peer_logical(s, p, which[i]) + (col - p.xs0) * H;
+            tfs::k_copy_f4<<<gb, 256, 0, s->stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), n4);
+            s->launches++;
+        }
+        // the left rank sees this as "from R", the right rank as "from L"
+        tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(p.base, p.lay, side == 0 ? flag_from_r_idx : flag_from_l_idx), seq);
+        s->launches++;
+    }
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+int flags_wait(tfs_sim *s, int idx_from_l, int idx_from_r, long long value) {
+    const long long *fl = s->peerL.present ? sync_slot(s->arena, s->lay, idx_from_l) : nullptr;
+    const long long *fr = s->peerR.present ? sync_slot(s->arena, s->lay, idx_from_r) : nullptr;
+    if (!fl && !fr) return TFS_OK;
+    tfs::k_flag_wait2<<<1, 1, 0, s->stream>>>(fl, fr, value);
+    s->launches++;
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+int flags_signal(tfs_sim *s, int idx_for_left_rank, int idx_for_right_rank, long long value) {
+    if (s->peerL.present) { tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(s->peerL.base, s->peerL.lay, idx_for_left_rank), value); s->launches++; }
+    if (s->peerR.present) { tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(s->peerR.base, s->peerR.lay, idx_for_right_rank), value); s->launches++; }
+    CU(cudaGetLastError());
+    return TFS_OK;
+}
+
+// One step of an x-slab handle.  Everything is asynchronous on the stream; cross-rank ordering is by
+// sequence flags in device memory (no host synchronisation, so ranks may also share one host thread):
+//   P  wait pushB(seq-1) from the right rank (u halo column of the post-advection field); projection;
+//      raise projdone(seq) at the left rank, wait for the right rank's projdone(seq)
+//   A1 wait advdone(seq-1) from both; push post-projection u, v halos; raise pushA(seq)
+//   A2 wait pushA(seq) from both; advect the owned columns
+//   A3 raise advdone(seq); push post-advection u, v, s halos; raise pushB(seq)
+int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
+    NEED(s->attached, TFS_ERR_COMM, "x-slab handle: call tfs_peer_attach before stepping");
+    NEED(s->opt.iterations > 0, TFS_ERR_INVALID_ARG, "x-slab handles need iterations >= 1");
+    const long long seq = ++s->step_seq;
+    int rc = flags_wait(s, SYNC_PUSHB_FROM_L, SYNC_PUSHB_FROM_R, seq - 1);
+    if (rc) return rc;
+    if (ev) CU(cudaEventRecord(ev[1], s->stream));
+    bool gravity_done = false;
+    rc = phase_project(s, dt, true, &gravity_done);
+    if (rc) return rc;
+    if (!gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
+    if (ev) CU(cudaEventRecord(ev[2], s->stream));
+    const int uv[2] = {0, 1}, uvs[3] = {0, 1, 3};
+    // The right rank's first band writes the final values of my last KB-1 owned columns (and my first
+    // halo column) straight into my memory: my projection result is complete only once ITS kernel is.
+    if (s->peerL.present) {
+        tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(s->peerL.base, s->peerL.lay, SYNC_PROJDONE_FROM_R), seq);
+        s->launches++;
+    }
+    if (s->peerR.present) {
+        tfs::k_flag_wait2<<<1, 1, 0, s->stream>>>(nullptr, sync_slot(s->arena, s->lay, SYNC_PROJDONE_FROM_R), seq);
+        s->launches++;
+    }
+    rc = flags_wait(s, SYNC_ADVDONE_FROM_L, SYNC_ADVDONE_FROM_R, seq - 1);
+    if (rc) return rc;
+    rc = halo_push(s, uv, 2, SYNC_PUSHA_FROM_R, SYNC_PUSHA_FROM_L, seq);
+    if (rc) return rc;
+    rc = flags_wait(s, SYNC_PUSHA_FROM_L, SYNC_PUSHA_FROM_R, seq);
+    if (rc) return rc;
+    rc = phase_advect(s, dt);
+    if (rc) return rc;
+    rc = flags_signal(s, SYNC_ADVDONE_FROM_R, SYNC_ADVDONE_FROM_L, seq);
+    if (rc) return rc;
+    rc = halo_push(s, uvs, 3, SYNC_PUSHB_FROM_R, SYNC_PUSHB_FROM_L, seq);
+    if (rc) return rc;
+    if (ev) CU(cudaEventRecord(ev[3], s->stream));
     return TFS_OK;
 }
 
@@ -408,6 +656,18 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
     if (cfg) s->cfg = *cfg;
     s->W = width;
     s->H = height;
+    s->rank = o.rank;
+    s->world = o.world;
+    {
+        const SlabGeom g = slab_geom((long long)width, o.rank, o.world);
+        s->c_lo = g.c_lo; s->c_hi = g.c_hi; s->xs0 = g.xs0; s->ncols = g.xs1 - g.xs0; s->b0 = g.b0; s->b0_next = g.b0_next;
+    }
+    if (o.world > 1) {
+        if (height % 4 != 0) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles need height %% 4 == 0"); }
+        if ((long long)width * (long long)height >= (1LL << 31) - (1LL << 20)) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles need width*height < 2^31"); }
+        if (s->b0_next >= 0 && s->b0_next <= s->b0) { delete s; return fail(TFS_ERR_INVALID_ARG, "grid too narrow for this many slabs"); }
+        if (o.mode != TFS_MODE_WAVEFRONT_EXACT || o.kernel == TFS_KERNEL_DIAGONAL) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles run the exact systolic projection only"); }
+    }
 #define CREATE_TRY(x)         \
     do {                      \
         rc = (x);             \
@@ -425,7 +685,12 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
         CU(cudaMallocHost((void **)&s->h_pin, 16 * sizeof(float)));
         return TFS_OK;
     }());
-    CREATE_TRY(alloc_fields(s, width * height));
+    CREATE_TRY(alloc_fields(s, (size_t)s->n()));
+    CREATE_TRY([&]() -> int {
+        CU(cudaMalloc((void **)&s->d_oob, sizeof(int)));
+        CU(cudaMemsetAsync(s->d_oob, 0, sizeof(int), s->stream));
+        return TFS_OK;
+    }());
     CREATE_TRY(reset_fields(s));
     // make_block_grid (simulator.rs:113-119): the left border column is solid
     tfs::k_fill_range_u8<<<blocks_for((long long)std::min(height, width * height), 256), 256, 0, s->stream>>>(
@@ -452,6 +717,9 @@ int tfs_destroy(tfs_sim *s) {
     if (s->d_part) cudaFree(s->d_part);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->d_stage) cudaFree(s->d_stage);
+    if (s->d_oob) cudaFree(s->d_oob);
+    if (s->peerL.present && s->peerL.ipc) cudaIpcCloseMemHandle(s->peerL.base);
+    if (s->peerR.present && s->peerR.ipc) cudaIpcCloseMemHandle(s->peerR.base);
     if (s->prof_created)
         for (int i = 0; i < kMaxProfSteps; ++i)
             for (int j = 0; j < 4; ++j) cudaEventDestroy(s->prof_ev[i][j]);
@@ -466,6 +734,7 @@ int tfs_resize(tfs_sim *s, size_t width, size_t height) {
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
     NEED(width >= 1 && height >= 1, TFS_ERR_INVALID_ARG, "width and height must be >= 1");
     NEED(width <= (1u << 24) && height <= (1u << 24), TFS_ERR_INVALID_ARG, "grid side exceeds 2^24");
+    NEED(!s->slab(), TFS_ERR_INVALID_ARG, "resize is not available on x-slab handles (create new handles instead)");
     int rc = set_device(s);
     if (rc) return rc;
     const size_t n_old = s->W * s->H, n_new = width * height, old_h = s->H;
@@ -555,8 +824,11 @@ int tfs_set_block(tfs_sim *s, size_t x, size_t y, int value) {
         return fail(TFS_ERR_OUT_OF_RANGE, "index out of bounds: the len is %zu but the index is %zu", s->W * s->H, idx);
     int rc = set_device(s);
     if (rc) return rc;
-    CU(cudaMemsetAsync(s->m + idx, value ? 1 : 0, 1, s->stream));
-    s->flags_dirty = true;
+    const long long lidx = (long long)idx - s->xs0 * (long long)s->H;
+    if (lidx >= 0 && lidx < s->n()) {  // a slab keeps only its own columns (+ halos); every rank gets every edit
+        CU(cudaMemsetAsync(s->m + lidx, value ? 1 : 0, 1, s->stream));
+        s->flags_dirty = true;
+    }
     return TFS_OK;
 }
 
@@ -567,9 +839,17 @@ int tfs_upload_blocks(tfs_sim *s, const uint8_t *mask, size_t offset, size_t n) 
     if (n == 0) return TFS_OK;
     int rc = set_device(s);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(s->m + offset, mask, n, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaStreamSynchronize(s->stream));  // the caller's buffer is not retained past the call
-    s->flags_dirty = true;
+    {
+        // clip the GLOBAL range [offset, offset+n) to the stored columns
+        const long long lo = std::max((long long)offset, s->xs0 * (long long)s->H);
+        const long long hi = std::min((long long)(offset + n), (s->xs0 + s->ncols) * (long long)s->H);
+        if (hi > lo) {
+            CU(cudaMemcpyAsync(s->m + (lo - s->xs0 * (long long)s->H), mask + (lo - (long long)offset), (size_t)(hi - lo),
+                               cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream));  // the caller's buffer is not retained past the call
+            s->flags_dirty = true;
+        }
+    }
     return TFS_OK;
 }
 
@@ -590,6 +870,7 @@ int tfs_step(tfs_sim *s, float dt) {
         ev = s->prof_ev[s->prof_n++];
         CU(cudaEventRecord(ev[0], s->stream));
     }
+    if (s->slab()) return step_slab(s, dt, ev);
     // gravity folds into the systolic projection's first load of v when that kernel runs
     const bool exact = s->opt.mode == TFS_MODE_WAVEFRONT_EXACT;
     const bool want_systolic = exact && tfs::systolic_available() &&
@@ -613,16 +894,19 @@ int tfs_step(tfs_sim *s, float dt) {
 
 int tfs_phase_gravity(tfs_sim *s, float dt) {
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    NEED(!s->slab(), TFS_ERR_INVALID_ARG, "x-slab handles step as a whole (tfs_step)");
     int rc = set_device(s);
     return rc ? rc : phase_gravity(s, dt);
 }
 int tfs_phase_project(tfs_sim *s, float dt) {
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    NEED(!s->slab(), TFS_ERR_INVALID_ARG, "x-slab handles step as a whole (tfs_step)");
     int rc = set_device(s);
     return rc ? rc : phase_project(s, dt, false, nullptr);
 }
 int tfs_phase_advect(tfs_sim *s, float dt) {
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
+    NEED(!s->slab(), TFS_ERR_INVALID_ARG, "x-slab handles step as a whole (tfs_step)");
     int rc = set_device(s);
     return rc ? rc : phase_advect(s, dt);
 }
@@ -639,6 +923,9 @@ int tfs_read_view(tfs_sim *s, int field, size_t x0, size_t y0, size_t w, size_t 
     NEED(s && dst, TFS_ERR_INVALID_ARG, "NULL argument");
     if (x0 > s->W || w > s->W - x0 || y0 > s->H || h > s->H - y0)
         return fail(TFS_ERR_OUT_OF_RANGE, "view [%zu+%zu) x [%zu+%zu) exceeds the %zu x %zu grid", x0, w, y0, h, s->W, s->H);
+    if ((long long)x0 < s->xs0 || (long long)(x0 + w) > s->xs0 + s->ncols)
+        return fail(TFS_ERR_OUT_OF_RANGE, "view columns [%zu, %zu) are not stored on this slab ([%lld, %lld))", x0, x0 + w, s->xs0,
+                    s->xs0 + s->ncols);
     int rc = set_device(s);
     if (rc) return rc;
     if (field == TFS_FIELD_FLAGS) {
@@ -651,7 +938,7 @@ int tfs_read_view(tfs_sim *s, int field, size_t x0, size_t y0, size_t w, size_t 
     if (rc) return rc;
     if (w == 0 || h == 0) return TFS_OK;
     if (h == s->H) {  // full-height window: columns are contiguous, no packing needed
-        CU(cudaMemcpyAsync(dst, (char *)src + x0 * s->H * elem, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(dst, (char *)src + (x0 - (size_t)s->xs0) * s->H * elem, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
     } else {
         rc = ensure_stage(s, w * h * elem);
         if (rc) return rc;
@@ -667,13 +954,20 @@ int tfs_read_view(tfs_sim *s, int field, size_t x0, size_t y0, size_t w, size_t 
         CU(cudaMemcpyAsync(dst, s->d_stage, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
+    {
+        int oob = 0;
+        CU(cudaMemcpy(&oob, s->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
+        if (oob) return fail(TFS_ERR_OUT_OF_RANGE, "an advection back-trace left the slab's %lld halo columns (|velocity|*dt too large)", kHalo);
+    }
     return TFS_OK;
 }
 
+// single GPU: the whole field (n = width*height).  x-slab handle: the OWNED columns only
+// (n = (c_hi - c_lo)*height, see tfs_get_slab); the caller concatenates the ranks.
 int tfs_read_field(tfs_sim *s, int field, void *dst, size_t n) {
     NEED(s && dst, TFS_ERR_INVALID_ARG, "NULL argument");
-    NEED(n == s->W * s->H, TFS_ERR_INVALID_ARG, "n must equal width*height");
-    return tfs_read_view(s, field, 0, 0, s->W, s->H, dst);
+    NEED(n == (size_t)(s->c_hi - s->c_lo) * s->H, TFS_ERR_INVALID_ARG, "n must equal (owned columns)*height");
+    return tfs_read_view(s, field, (size_t)s->c_lo, 0, (size_t)(s->c_hi - s->c_lo), s->H, dst);
 }
 
 int tfs_write_field(tfs_sim *s, int field, const void *src, size_t n) {
@@ -686,7 +980,8 @@ int tfs_write_field(tfs_sim *s, int field, const void *src, size_t n) {
     size_t elem = 0;
     rc = field_ptr(s, field, &dst, &elem);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(dst, src, n * elem, cudaMemcpyHostToDevice, s->stream));
+    // `src` is always the GLOBAL field; a slab copies its stored columns (owned + halos), so no exchange is needed
+    CU(cudaMemcpyAsync(dst, (const char *)src + (size_t)s->xs0 * s->H * elem, (size_t)s->n() * elem, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     if (field == TFS_FIELD_M) s->flags_dirty = true;
     return TFS_OK;
@@ -696,9 +991,9 @@ int tfs_pressure_minmax(tfs_sim *s, float *min_p, float *max_p) {
     NEED(s && min_p && max_p, TFS_ERR_INVALID_ARG, "NULL argument");
     int rc = set_device(s);
     if (rc) return rc;
-    const long long n = s->n();
+    const long long n = (s->c_hi - s->c_lo) * (long long)s->H;  // owned columns (a slab reports its own share)
     const int nb = (int)std::min<long long>(blocks_for(n, 256 * 8), 2048);
-    tfs::k_minmax_partial<<<nb, 256, 0, s->stream>>>(s->p, n, s->d_part);
+    tfs::k_minmax_partial<<<nb, 256, 0, s->stream>>>(s->p + (s->c_lo - s->xs0) * (long long)s->H, n, s->d_part);
     tfs::k_minmax_final<<<1, 256, 0, s->stream>>>(s->d_part, nb, s->d_part + 2 * 4096 - 2);
     s->launches += 2;
     CU(cudaGetLastError());
@@ -710,7 +1005,7 @@ int tfs_pressure_minmax(tfs_sim *s, float *min_p, float *max_p) {
     // running minimum is not offered to the maximum.  p[0] and p[1] are always 0.0 when H >= 2
     // (border cells are never written), after which the rule equals plain min/max; the only grid
     // where it differs is the single-cell one, where max stays f32::MIN.
-    if (n == 1) *max_p = -3.402823466e38f;
+    if (s->gn() == 1) *max_p = -3.402823466e38f;
     return TFS_OK;
 }
 
@@ -722,7 +1017,7 @@ int tfs_divergence_linf(tfs_sim *s, float *out) {
     if (rc) return rc;
     const long long n = s->n();
     const int nb = (int)std::min<long long>(blocks_for(n, 256 * 8), 2048);
-    tfs::k_div_partial<<<nb, 256, 0, s->stream>>>(s->u, s->v, s->flags, s->grid(), 0, (long long)s->W, s->d_part);
+    tfs::k_div_partial<<<nb, 256, 0, s->stream>>>(s->u, s->v, s->flags, s->grid(), s->c_lo - s->xs0, s->c_hi - s->xs0, s->d_part);
     tfs::k_minmax_final<<<1, 256, 0, s->stream>>>(s->d_part, nb, s->d_part + 2 * 4096 - 2);
     s->launches += 2;
     CU(cudaGetLastError());
@@ -846,13 +1141,85 @@ int tfs_selftest_division(int device, uint64_t *mismatches) {
 
 int tfs_peer_export(tfs_sim *s, void *blob) {
     NEED(s && blob, TFS_ERR_INVALID_ARG, "NULL argument");
-    return fail(TFS_ERR_COMM, "multi-slab handles are not available in this build");
+    NEED(s->slab(), TFS_ERR_INVALID_ARG, "not an x-slab handle (options.world == 1)");
+    int rc = set_device(s);
+    if (rc) return rc;
+    PeerBlob b{};
+    b.magic = kBlobMagic;
+    b.rank = s->rank; b.world = s->world; b.device = s->device;
+    b.W = (long long)s->W; b.H = (long long)s->H; b.xs0 = s->xs0; b.ncols = s->ncols; b.c_lo = s->c_lo; b.c_hi = s->c_hi;
+    b.b0 = s->b0; b.b0_next = s->b0_next;
+    b.pid = (unsigned long long)getpid();
+    b.raw_ptr = (unsigned long long)(uintptr_t)s->arena;
+    CU(cudaIpcGetMemHandle(&b.handle, s->arena));
+    memset(blob, 0, TFS_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return TFS_OK;
 }
+
+namespace {
+int attach_one(tfs_sim *s, tfs_sim::Peer &p, const void *blob, int expect_rank) {
+    PeerBlob b;
+    memcpy(&b, blob, sizeof(b));
+    NEED(b.magic == kBlobMagic, TFS_ERR_COMM, "peer blob: bad magic");
+    NEED(b.world == s->world && b.rank == expect_rank, TFS_ERR_COMM, "peer blob: wrong rank/world");
+    NEED(b.W == (long long)s->W && b.H == (long long)s->H, TFS_ERR_COMM, "peer blob: grid size differs");
+    p.xs0 = b.xs0; p.ncols = b.ncols; p.c_lo = b.c_lo; p.c_hi = b.c_hi; p.b0 = b.b0; p.b0_next = b.b0_next;
+    p.lay = slab_layout(b.W, b.H, b.ncols, b.b0, b.b0_next);
+    if (b.pid == (unsigned long long)getpid()) {
+        // same process (one host thread driving several GPUs): plain peer access, no IPC
+        if (b.device != s->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s->device, b.device));
+            NEED(can, TFS_ERR_COMM, "devices cannot access each other's memory");
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(TFS_ERR_COMM, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        p.base = reinterpret_cast<char *>((uintptr_t)b.raw_ptr);
+        p.ipc = false;
+    } else {
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(TFS_ERR_COMM, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        p.base = reinterpret_cast<char *>(ptr);
+        p.ipc = true;
+    }
+    p.present = true;
+    return TFS_OK;
+}
+}  // namespace
+
 int tfs_peer_attach(tfs_sim *s, const void *left_blob, const void *right_blob) {
-    (void)left_blob;
-    (void)right_blob;
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
-    return fail(TFS_ERR_COMM, "multi-slab handles are not available in this build");
+    NEED(s->slab(), TFS_ERR_INVALID_ARG, "not an x-slab handle (options.world == 1)");
+    NEED((left_blob != nullptr) == (s->rank > 0), TFS_ERR_INVALID_ARG, "left blob: needed exactly when rank > 0");
+    NEED((right_blob != nullptr) == (s->rank < s->world - 1), TFS_ERR_INVALID_ARG, "right blob: needed exactly when rank < world-1");
+    int rc = set_device(s);
+    if (rc) return rc;
+    if (left_blob) { rc = attach_one(s, s->peerL, left_blob, s->rank - 1); if (rc) return rc; }
+    if (right_blob) { rc = attach_one(s, s->peerR, right_blob, s->rank + 1); if (rc) return rc; }
+    s->attached = true;
+    return TFS_OK;
+}
+
+int tfs_slab_bounds(size_t width, int rank, int world, size_t *c_lo, size_t *c_hi) {
+    NEED(c_lo && c_hi, TFS_ERR_INVALID_ARG, "NULL argument");
+    NEED(world >= 1 && rank >= 0 && rank < world && width >= 1, TFS_ERR_INVALID_ARG, "bad rank/world/width");
+    const SlabGeom g = slab_geom((long long)width, rank, world);
+    *c_lo = (size_t)g.c_lo;
+    *c_hi = (size_t)g.c_hi;
+    return TFS_OK;
+}
+
+int tfs_get_slab(const tfs_sim *s, size_t *c_lo, size_t *c_hi, size_t *stored_lo, size_t *stored_hi) {
+    NEED(s && c_lo && c_hi, TFS_ERR_INVALID_ARG, "NULL argument");
+    *c_lo = (size_t)s->c_lo;
+    *c_hi = (size_t)s->c_hi;
+    if (stored_lo) *stored_lo = (size_t)s->xs0;
+    if (stored_hi) *stored_hi = (size_t)(s->xs0 + s->ncols);
+    return TFS_OK;
 }
 
 }  // extern "C"

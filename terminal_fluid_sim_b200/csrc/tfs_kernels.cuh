@@ -256,9 +256,11 @@ k_advect(const float *__restrict__ u, const float *__restrict__ v, const float *
 TFS_DEVINL float fadd_f(float a, float b, float one) { return __fmaf_rn(a, one, b); }
 TFS_DEVINL float fsub_f(float a, float b, float one) { return __fmaf_rn(b, -one, a); }
 
-template <int FT>
+// SLAB: `f` is a global-column base (storage pointer - xs0*H); columns outside the stored range
+// [cs0, cs1] are clamped for memory safety and reported through *oob (halo too small for this dt).
+template <int FT, bool SLAB = false>
 TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, int W, int H, float Wf, float Hf,
-                                float one) {
+                                float one, unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
     const float dx = (FT == FT_U) ? 0.0f : 0.5f;   // simulator.rs:277-281
     const float dy = (FT == FT_V) ? 0.0f : 0.5f;
     x = fmaxf(fminf(x, Wf), 1.0f);                 // :271
@@ -270,9 +272,17 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
     const float ty = fsub_f(ys, (float)yb, one);                       // :289
     const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);  // :291-292
     // xr = min(xl+1, W-1), yt = min(yb+1, H-1) (:284, :288) as index offsets: +H / +1 unless clamped
-    const unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
+    unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
     const unsigned dyo = (yb < (unsigned)(H - 1)) ? 1u : 0u;
-    const unsigned i00 = xl * (unsigned)H + yb, i10 = i00 + dxo;
+    unsigned xls = xl;
+    if (SLAB) {
+        if (xl < cs0 || xl + (dxo ? 1u : 0u) > cs1) {
+            *oob = 1;  // benign race: every writer stores 1
+            xls = min(max(xl, cs0), cs1);
+            if (xls + 1u > cs1) dxo = 0u;
+        }
+    }
+    const unsigned i00 = xls * (unsigned)H + yb, i10 = i00 + dxo;
     const float f00 = __ldg(f + i00), f10 = __ldg(f + i10);
     const float f11 = __ldg(f + i10 + dyo), f01 = __ldg(f + i00 + dyo);
     return fadd_f(fadd_f(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11), one),
@@ -281,13 +291,16 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
 
 // blockDim.x threads along y (rows y0 .. y0+blockDim.x), CPB columns per block marched in +x so the
 // column i+1 values loaded for cell (i, j) are reused as "own" values of cell (i+1, j).
-template <int CPB>
+// SLAB: all pointers are global-column bases, only columns [c_begin, c_end) are advected, the
+// stored columns are [cs0, cs1].
+template <int CPB, bool SLAB = false>
 __global__ void __launch_bounds__(256)
 k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
            const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
-           float *__restrict__ ns, int W, int H, float dt, float one) {
+           float *__restrict__ ns, int W, int H, float dt, float one, int c_begin = 0, int c_end = 0x7fffffff,
+           unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i0 = blockIdx.y * CPB;
+    const int i0 = c_begin + blockIdx.y * CPB;
     if (j >= H) return;
     const float Wf = (float)W, Hf = (float)H;
     const float fj = (float)j, fjh = fadd(fj, 0.5f);
@@ -300,7 +313,7 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
 #pragma unroll
     for (int c = 0; c < CPB; ++c) {
         const int i = i0 + c;
-        if (i >= W) break;
+        if (i >= W || i >= c_end) break;
         // column i+1 (right); clamped at the right border for memory safety only
         const unsigned idr = (i + 1 < W) ? idx + (unsigned)H : idx;
         const float uR = u[idr], uRB = u[idr - j + jm], vR = v[idr], vRT = v[idr - j + jp];
@@ -315,19 +328,19 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
             const float avg_v = fmul(fadd_f(fadd(fadd(vL, vLT), vT), vC, one), 0.25f);
             float xp = fsub_f(fi, fmul(uC, dt), one);
             float yp = fsub_f(fjh, fmul(avg_v, dt), one);
-            un = sample_field32<FT_U>(u, xp, yp, W, H, Wf, Hf, one);
+            un = sample_field32<FT_U, SLAB>(u, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
             // v component (:216-224), avg_horizontal (:257-267)
             const float avg_u = fmul(fadd_f(fadd(fadd(uB, uRB), uR), uC, one), 0.25f);
             const float fih = fadd(fi, 0.5f);
             xp = fsub_f(fih, fmul(avg_u, dt), one);
             yp = fsub_f(fj, fmul(vC, dt), one);
-            vn = sample_field32<FT_V>(v, xp, yp, W, H, Wf, Hf, one);
+            vn = sample_field32<FT_V, SLAB>(v, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
             // smoke (:227-237)
             const float cv = fmul(fadd(vC, vT), 0.5f);
             const float cu = fmul(fadd(uC, uR), 0.5f);
             xp = fsub_f(fih, fmul(cu, dt), one);
             yp = fsub_f(fjh, fmul(cv, dt), one);
-            sn = sample_field32<FT_S>(s, xp, yp, W, H, Wf, Hf, one);
+            sn = sample_field32<FT_S, SLAB>(s, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
         }
         nu[idx] = un; nv[idx] = vn; ns[idx] = sn;
         // march: column i+1 becomes the own column, column i the left one
@@ -335,6 +348,24 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
         uC = uR; uB = uRB; vC = vR; vT = vRT;
         idx = idr;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x-slab halo exchange: plain peer copies plus sequence flags living in the RECEIVER's memory.
+__global__ void k_copy_f4(const float4 *__restrict__ src, float4 *__restrict__ dst, long long n4) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < n4; t += stride) dst[t] = src[t];
+}
+__global__ void k_flag_set(long long *flag, long long value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile long long *>(flag) = value;
+}
+__global__ void k_flag_wait2(const long long *f0, const long long *f1, long long value) {
+    // f0 / f1 may be null (no neighbour on that side)
+    if (f0) while (*reinterpret_cast<const volatile long long *>(f0) < value) {}
+    if (f1) while (*reinterpret_cast<const volatile long long *>(f1) < value) {}
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -584,16 +584,18 @@ struct SysLaunch {
         if ((e = cudaMemsetAsync(cnt, 0, n_cnt * sizeof(int), a.stream)) != cudaSuccess) return e;
         auto kern = k_project_systolic<KG, NW, S, D>;
         const size_t smem = smem_bytes();
-        static bool attr_set = false;
-        static int occ = 0;
-        if (!attr_set) {
+        static bool attr_set[64] = {false};  // function attributes are per device
+        static int occ_dev[64] = {0};
+        const int di = dev & 63;
+        if (!attr_set[di]) {
             if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
                 *msg = "cudaFuncSetAttribute(max dynamic smem)";
                 return e;
             }
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (NW + 1), smem)) != cudaSuccess) return e;
-            attr_set = true;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 1), smem)) != cudaSuccess) return e;
+            attr_set[di] = true;
         }
+        const int occ = occ_dev[di];
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
         const long long n_tasks = (long long)P.n_passes * P.n_bands;
         const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);

@@ -694,16 +694,18 @@ struct Sys4Launch {
         P4.n_tasks = (int)n_tasks;
         auto kern = k_project_systolic4<KG, NW, G>;
         const size_t smem = sizeof(Sys4Smem<KG, NW, G>) + 128;
-        static bool attr_set = false;
-        static int occ = 0;
-        if (!attr_set) {
+        static bool attr_set[64] = {false};  // function attributes are per device
+        static int occ_dev[64] = {0};
+        const int di = dev & 63;
+        if (!attr_set[di]) {
             if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
                 *msg = "cudaFuncSetAttribute(max dynamic smem)";
                 return e;
             }
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (NW + 2), smem)) != cudaSuccess) return e;
-            attr_set = true;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 2), smem)) != cudaSuccess) return e;
+            attr_set[di] = true;
         }
+        const int occ = occ_dev[di];
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
         const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
 #ifdef TFS_SYS_TRACE

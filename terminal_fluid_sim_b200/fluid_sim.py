@@ -43,11 +43,12 @@ class FluidSim:
 
     def __init__(self, width: int = 2, height: int = 2, config: SimConfig | None = None, *,
                  iterations: int = 50, omega: float = 1.9, mode: int = MODE_WAVEFRONT_EXACT,
-                 kernel: int = KERNEL_AUTO, temporal_block: int = 0, device: int = 0):
+                 kernel: int = KERNEL_AUTO, temporal_block: int = 0, device: int = 0,
+                 rank: int = 0, world: int = 1):
         self._L = _lib.load()
         self._h = C.c_void_p()
         cfg = (config or SimConfig())._c()
-        opt = TfsOptions(iterations, omega, mode, device, kernel, temporal_block, 0, 1)
+        opt = TfsOptions(iterations, omega, mode, device, kernel, temporal_block, rank, world)
         if width < 0 or height < 0:
             raise OverflowError("usize cannot be negative")
         check(self._L.tfs_create(width, height, C.byref(cfg), C.byref(opt), C.byref(self._h)))
@@ -145,10 +146,28 @@ class FluidSim:
     def _dtype(field):
         return np.uint8 if field in (FIELD_M, FIELD_FLAGS) else np.float32
 
+    def get_slab(self):
+        """(c_lo, c_hi, stored_lo, stored_hi): owned and stored global columns of this handle."""
+        a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(self._L.tfs_get_slab(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.PEER_BLOB_BYTES)
+        check(self._L.tfs_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, left: bytes | None, right: bytes | None):
+        lb = C.create_string_buffer(left, _lib.PEER_BLOB_BYTES) if left is not None else None
+        rb = C.create_string_buffer(right, _lib.PEER_BLOB_BYTES) if right is not None else None
+        check(self._L.tfs_peer_attach(self._h, lb, rb))
+
     def read_field(self, field: int, out: np.ndarray | None = None) -> np.ndarray:
-        w, h = self.get_size()
+        """whole field on a single-GPU handle; the OWNED columns on an x-slab handle"""
+        _, h = self.get_size()
+        c_lo, c_hi, _, _ = self.get_slab()
         if out is None:
-            out = np.empty(w * h, self._dtype(field))
+            out = np.empty((c_hi - c_lo) * h, self._dtype(field))
         check(self._L.tfs_read_field(self._h, field, out.ctypes.data, out.size))
         return out
 
@@ -263,3 +282,39 @@ def selftest_division(device: int = 0) -> int:
     n = C.c_uint64()
     check(_lib.load().tfs_selftest_division(device, C.byref(n)))
     return n.value
+
+
+def slab_bounds(width: int, rank: int, world: int):
+    """columns [c_lo, c_hi) owned by `rank` of `world` (host arithmetic, no device needed)"""
+    a, b = C.c_size_t(), C.c_size_t()
+    check(_lib.load().tfs_slab_bounds(width, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+class SlabGroup:
+    """All x-slabs of one grid driven from ONE host thread (one handle per visible GPU).  `next_step`
+    only enqueues work, so the ranks overlap on their devices; used by the multi-GPU tests and
+    when a single process owns several GPUs.  With one process per GPU (torchrun) use
+    `FluidSim(..., rank=, world=)` + `peer_export` / `peer_attach` directly (see bench.py)."""
+
+    def __init__(self, width, height, config=None, *, world, devices=None, **kw):
+        devices = list(devices) if devices is not None else list(range(world))
+        self.sims = [FluidSim(width, height, config, rank=r, world=world, device=devices[r], **kw) for r in range(world)]
+        blobs = [s.peer_export() for s in self.sims]
+        for r, s in enumerate(self.sims):
+            s.peer_attach(blobs[r - 1] if r > 0 else None, blobs[r + 1] if r < world - 1 else None)
+
+    def each(self, name, *a, **k):
+        return [getattr(s, name)(*a, **k) for s in self.sims]
+
+    def next_step(self, dt):
+        self.each("next_step", dt)
+
+    def sync(self):
+        self.each("sync")
+
+    def read_field(self, field):
+        return np.concatenate([s.read_field(field) for s in self.sims])
+
+    def close(self):
+        self.each("close")
