@@ -145,9 +145,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
 
     if world > 1:
-        # x-slab decomposition is not wired into this bench yet: every rank runs an independent replica
-        # of an equal share of the columns' worth of work.  Reported honestly as replicas.
-        raise SystemExit("multi-GPU slabs are not available in this build of bench.py")
+        return run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src)
 
     sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank)
     setup_scene(sim, wl)
@@ -254,6 +252,104 @@ def run_ours(args):
     }
     if rank == 0:
         print(json.dumps(out))
+
+
+def run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src):
+    """N > 1: one x-slab per rank / GPU.  Neighbours exchange halo columns, band records and progress
+    counters by direct peer stores over NVLink (CUDA IPC mappings); torch.distributed is used only to
+    hand the IPC blobs around, for the barrier and for the max-over-ranks of the device time."""
+    import torch
+    W, H, K = wl["W"], wl["H"], wl["K"]
+    sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank, rank=rank, world=world)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, sim.peer_export())
+    sim.peer_attach(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+    setup_scene(sim, wl)
+    sim.sync()
+    dist.barrier()
+    for _ in range(args.warmup):
+        sim.next_step(DT)
+    sim.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sim.set_profiling(True)
+    l_before = sim.launch_count()
+    ms = time_steps(sim, args.steps)
+    l_after = sim.launch_count()
+    phases = sim.phase_ms()
+    sim.set_profiling(False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ms, phases["project_ms"] / max(1, phases["steps"]), phases["advect_ms"] / max(1, phases["steps"])],
+                     dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, proj_ms, adv_ms = (float(x) for x in t.tolist())
+    clocks = sampler.stop() if rank == 0 else None
+    cells = W * H
+    value = cells * args.steps / (ms / 1e3) / 1e9
+    alg_bytes = 25.0 * K * cells
+    achieved = alg_bytes / (proj_ms / 1e3) / 1e9          # whole job, all GPUs
+    roofline = {"kernel": "k_project_systolic4 (gravity + %d-iteration exact projection), %d x-slabs" % (K, world),
+                "bound": "hbm", "achieved": round(achieved / world, 1), "peak": peak, "unit": "GB/s (per GPU)",
+                "frac": round(achieved / world / peak, 4), "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": round(proj_ms, 4), "algorithmic_bytes_per_launch": alg_bytes / world,
+                "advect": {"ms_per_launch": round(adv_ms, 4)}}
+    # e2e: every rank reads its share of the visible window (rank 0 owns the left columns the renderer shows)
+    c_lo, c_hi, _, _ = sim.get_slab()
+    vx, vy, vw, vh = view_window(W, H)
+    vw_r = max(0, min(vx + vw, c_hi) - max(vx, c_lo))
+    pin_s, pin_p = tfs.PinnedBuffer(max(1, vw_r * vh)), tfs.PinnedBuffer(max(1, vw_r * vh))
+    pin_m = tfs.PinnedBuffer(H, np.uint8)
+
+    def e2e_step(i):
+        x = 8 + (i % 8)
+        pin_m.array[:] = 0
+        pin_m.array[H // 2 - 4:H // 2 + 4] = 1
+        sim.upload_blocks(pin_m.array, offset=x * H)
+        sim.next_step(DT)
+        if vw_r > 0:
+            sim.read_view(tfs.FIELD_S, max(vx, c_lo), vy, vw_r, vh, out=pin_s.array)
+            sim.read_view(tfs.FIELD_P, max(vx, c_lo), vy, vw_r, vh, out=pin_p.array)
+        return sim.pressure_minmax()
+
+    e2e_step(0)
+    sim.sync()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(max(1, args.steps)):
+        e2e_step(i + 1)
+    sim.sync()
+    dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e = {"value": round(cells * max(1, args.steps) / e2e_s / 1e9, 4), "unit": "Gcell-steps/s",
+           "h2d_bytes_per_step": int(H), "d2h_bytes_per_step": int(2 * vw * vh * 4 + 8 * world),
+           "what": "per rank: upload_blocks(1 column) + next_step + read_view(own share of the %dx%d smoke/pressure window) "
+                   "+ pressure_minmax; host wall clock, max over ranks" % (vw, vh)}
+    launches_per_step = (l_after - l_before) / max(1, args.steps)
+    pin_s.close(); pin_p.close(); pin_m.close()
+    sim.sync()
+    dist.barrier()
+    sim.close()
+    out = {
+        "metric": "Gcell-steps/s", "value": round(value, 4), "unit": "Gcell-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "grid": [W, H], "pressure_iterations": K, "mode": "wavefront_exact",
+                   "omega": 1.9, "parallelism": "x-slabs x%d (peer stores over NVLink, no collective)" % world,
+                   "l2": "state (%.1f GB) exceeds L2, no flush needed" % (17 * cells / 1e9)},
+        "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
+        "gpu_launches": int(round(launches_per_step * args.steps)) * world, "gpu_launches_per_step_per_rank": launches_per_step,
+        "clocks": clocks, "extra": {},
+    }
+    if rank == 0:
+        print(json.dumps(out))
+    dist.destroy_process_group()
 
 
 def cpu_sample(workload):
