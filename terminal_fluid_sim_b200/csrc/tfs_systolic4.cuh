@@ -669,7 +669,7 @@ struct Sys4Launch {
         // key, on this rank and on its neighbours alike.
         const long long n_tasks = (long long)P.n_passes * SL.nb_local;
         if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands ||
-            ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB) {
+            ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB || getenv("TFS_SYS_ORDER")) {
             if (ws4.n_tasks_cap < (size_t)n_tasks) {
                 if (ws4.d_tasks) cudaFree(ws4.d_tasks);
                 if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
@@ -678,7 +678,18 @@ struct Sys4Launch {
                 if ((e = cudaMallocHost((void **)&ws4.h_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
                 ws4.n_tasks_cap = (size_t)n_tasks;
             }
-            const int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
+            // Issue order.  "diag": key = start time (a band trails its left neighbour by ~lag_b steps, the
+            // previous pass by ~lag_t): all passes advance together, good when every task is resident.
+            // "lex": pass-major.  With more tasks than CTA slots the diagonal order makes the band chain of
+            // pass 0 wait behind later passes of earlier bands, which serialises the GPUs of a slab run
+            // (rank r+1 cannot start before rank r's LAST band runs); pass-major lets pass 0 sweep first.
+            int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
+            {
+                const char *ord = getenv("TFS_SYS_ORDER");
+                const long long slots = (long long)ws.num_sms * 2;
+                const bool lex = ord ? (ord[0] == 'l') : (ext != nullptr && n_tasks > slots);
+                if (lex) lag_t = 1 << 24;
+            }
             std::vector<std::pair<long long, int2>> v;
             v.reserve((size_t)n_tasks);
             for (int tb = 0; tb < P.n_passes; ++tb)
