@@ -684,17 +684,21 @@ struct Sys4Launch {
             // pass 0 wait behind later passes of earlier bands, which serialises the GPUs of a slab run
             // (rank r+1 cannot start before rank r's LAST band runs); pass-major lets pass 0 sweep first.
             int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
+            bool hybrid = false;  // pass 0 first (feeds the next rank's bands), later passes in start-time order
             {
                 const char *ord = getenv("TFS_SYS_ORDER");
                 const long long slots = (long long)ws.num_sms * 2;
+                // measured on 8 B200 at 32768^2, K=200: pass-major 190 ms/step, hybrid 505, start-time 524
                 const bool lex = ord ? (ord[0] == 'l') : (ext != nullptr && n_tasks > slots);
+                hybrid = ord ? (ord[0] == 'h') : false;
                 if (lex) lag_t = 1 << 24;
             }
             std::vector<std::pair<long long, int2>> v;
             v.reserve((size_t)n_tasks);
             for (int tb = 0; tb < P.n_passes; ++tb)
                 for (int b = SL.b0; b < SL.b0 + SL.nb_local; ++b)
-                    v.push_back({(long long)b * lag_b + (long long)tb * lag_t, make_int2(tb, b)});
+                    v.push_back({(long long)b * lag_b + (long long)tb * lag_t + ((hybrid && tb > 0) ? (long long)SL.nb_local * lag_b : 0LL),
+                                 make_int2(tb, b)});
             std::stable_sort(v.begin(), v.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
             for (size_t i = 0; i < v.size(); ++i) ws4.h_tasks[i] = v[i].second;
             if ((e = cudaMemcpyAsync(ws4.d_tasks, ws4.h_tasks, (size_t)n_tasks * sizeof(int2), cudaMemcpyHostToDevice, a.stream)) != cudaSuccess) return e;

@@ -1,0 +1,67 @@
+"""Multi-GPU x-slab tests (need >= 2 CUDA devices; skipped otherwise): the slab handles, driven from
+one host thread, must reproduce the CPU oracle bit-for-bit, i.e. also the single-GPU result."""
+import numpy as np
+import pytest
+
+import terminal_fluid_sim_b200 as tfs
+from oracle.oracle import OracleSim, frac_to_threshold
+from tests.helpers import DT, bits_equal, first_mismatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+FIELDS = ((tfs.FIELD_U, "u"), (tfs.FIELD_V, "v"), (tfs.FIELD_P, "p"), (tfs.FIELD_S, "s"))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("W,H,K,tb,g", [(256, 64, 4, 4, 0.0), (520, 96, 50, 0, 9.8), (1024, 256, 40, 16, 0.0)])
+def test_slabs_match_oracle_bit_exact(world, W, H, K, tb, g):
+    if _ndev() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if (W + 1 + 31) // 32 < world:
+        pytest.skip("grid too narrow for this many slabs")
+    grp = tfs.SlabGroup(W, H, tfs.SimConfig(gravity=g), world=world, iterations=K, temporal_block=tb)
+    o = OracleSim(W, H, gravity=g, iterations=K)
+    thr = frac_to_threshold(0.05)
+    grp.each("scene_random", 77, thr); o.L.orc_scene_random(o.h, 77, thr)
+    grp.each("fill_random_velocity", 5, 60.0); o.fill_random_velocity(5, 60.0)
+    assert np.array_equal(grp.read_field(tfs.FIELD_M), o.m)
+    # the slabs tile the grid exactly
+    bounds = [s.get_slab()[:2] for s in grp.sims]
+    assert bounds[0][0] == 0 and bounds[-1][1] == W and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+    for st in range(3):
+        grp.next_step(DT); o.step(DT)
+        grp.sync()
+        for f, n in FIELDS:
+            a, b = grp.read_field(f), getattr(o, n)
+            assert bits_equal(a, b), f"world={world} step {st} {n}: " + first_mismatch(a, b, H)
+    # edits reach every slab that stores the cell; results stay exact afterwards
+    x = bounds[0][1]  # first column of slab 1: stored by slabs 0 (halo) and 1 (owned)
+    grp.each("set_block", x, H // 2); o.set_block(x, H // 2)
+    grp.next_step(DT); o.step(DT); grp.sync()
+    for f, n in FIELDS:
+        assert bits_equal(grp.read_field(f), getattr(o, n)), n
+    grp.close()
+
+
+def test_slab_handle_rejects_what_it_cannot_do():
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    with pytest.raises(tfs.TfsError):
+        tfs.FluidSim(256, 66, rank=0, world=2)              # H % 4 != 0
+    with pytest.raises(tfs.TfsError):
+        tfs.FluidSim(40, 64, rank=0, world=4)               # fewer bands than slabs
+    s = tfs.FluidSim(256, 64, rank=0, world=2)
+    with pytest.raises(tfs.TfsError):
+        s.next_step(DT)                                     # not attached yet
+    with pytest.raises(tfs.TfsError):
+        s.resize(128, 64)
+    s.close()
