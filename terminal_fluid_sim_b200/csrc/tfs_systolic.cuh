@@ -637,7 +637,7 @@ inline bool systolic_available() { return true; }
 // (KG, NW) shapes that are instantiated; KB = KG*NW iterations are fused per pass.
 struct SysShape { int kg, nw; };
 inline const SysShape *systolic_shapes(int *n) {
-    static const SysShape shapes[] = {{6, 4}, {4, 8}, {4, 4}, {4, 3}, {2, 5}, {4, 2}, {2, 8}, {2, 4}, {2, 2}, {5, 2}, {1, 8}, {8, 2}, {8, 4}, {8, 1}};
+    static const SysShape shapes[] = {{4, 4}, {6, 4}, {4, 8}, {4, 3}, {2, 5}, {4, 2}, {2, 8}, {2, 4}, {2, 2}, {5, 2}, {1, 8}, {8, 2}, {8, 4}, {8, 1}};
     *n = (int)(sizeof(shapes) / sizeof(shapes[0]));
     return shapes;
 }
@@ -665,7 +665,7 @@ inline SysShape systolic_pick(int iterations, int requested) {
     double best_cost = 1e30;
     for (int i = 0; i < n; ++i) {
         const int kb = sh[i].kg * sh[i].nw;
-        if (kb > 32) continue;
+        if (kb > 16 || sh[i].nw > 4) continue;  // measured on B200: (4,4) with 16-row rings (3 CTAs/SM) wins or ties at every K tried
         const int passes = (iterations + kb - 1) / kb;
         const double cost = passes * (kb + 16.0);  // measured on B200: a pass costs ~16 iterations' worth of fixed latency
         if (cost < best_cost - 1e-9) { best_cost = cost; best = sh[i]; }

@@ -81,19 +81,22 @@ TFS_DEVINL int prog_of(long long v, long long seq) {
 }
 TFS_DEVINL long long prog_make(long long seq, int x) { return (seq << 32) | (long long)(unsigned)x; }
 
-template <int KG, int NW, int G>
+// RB = rows per block of the input / output rings: 32 (3 slots, 96 ring rows) or 16 (4 slots, 64 ring rows:
+// 24 KB less shared memory per CTA, which is what lets a third CTA fit on an SM).
+template <int KG, int NW, int G, int RB>
 struct Sys4Smem {
-    static constexpr int NS_IN = 3, NS_OUT = 3, NR = 3, NPH = 4;
-    // row rings: [column][slot*32 + row-in-block]; 32*NS rows per column, bank = row & 31
-    float in_u[32][32 * NS_IN];
-    float in_v[32][32 * NS_IN];
-    float in_p[32][32 * NS_IN];
-    float out_u[32][32 * NS_OUT];
-    float out_v[32][32 * NS_OUT];
-    float out_p[32][32 * NS_OUT];
+    static constexpr int NS_IN = (RB == 32) ? 3 : 4, NS_OUT = NS_IN, NR = 3, NPH = 4;
+    static constexpr int RIN = RB * NS_IN, ROUT = RB * NS_OUT;
+    // row rings: [column][ring row]; the ring length is a multiple of 32, so bank = row & 31
+    float in_u[32][RIN];
+    float in_v[32][RIN];
+    float in_p[32][RIN];
+    float out_u[32][ROUT];
+    float out_v[32][ROUT];
+    float out_p[32][ROUT];
     float4 grp[2][NW][32];
     float4 rec[NR][NW][G][KG];
-    unsigned char in_f[32][32 * NS_IN + 4];  // +4: odd word pitch, fewer bank conflicts on the diagonal byte reads
+    unsigned char in_f[32][RIN + 4];  // +4: odd word pitch, fewer bank conflicts on the diagonal byte reads
     unsigned long long in_full[NS_IN], in_empty[NS_IN];
     unsigned long long rec_full[NR], rec_empty[NR];
     unsigned long long rec_written[NPH], pub_done[NPH];
@@ -101,13 +104,14 @@ struct Sys4Smem {
     int task;
 };
 
-template <int KG, int NW, int G>
-__global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params P4) {
-    using SM = Sys4Smem<KG, NW, G>;
+template <int KG, int NW, int G, int RB>
+__global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
+    using SM = Sys4Smem<KG, NW, G, RB>;
+    static_assert(RB == 16 || RB == 32, "ring blocks are 16 or 32 rows");
+    static_assert(RB % G == 0, "a ring block is a whole number of record intervals");
     constexpr int KB = KG * NW;
     constexpr int NCT = 32 * NW;
     constexpr int NS_IN = SM::NS_IN, NS_OUT = SM::NS_OUT, NR = SM::NR, NPH = SM::NPH;
-    static_assert(32 % G == 0, "a 32-row block is a whole number of record intervals");
     static_assert(KG >= 1 && KG <= 8, "a k-group's flags are packed 4 bits per iteration into 32 bits");
     const SysParams &P = P4.base;
 
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
         const size_t rec_stride = (size_t)P.n_rec * KG;  // float4 per (band, k-group)
         const int T = P.T;
         const int n_int = (T + G - 1) / G;                 // record intervals
-        const int n_blk_in = (int)((H + 31) >> 5);          // field blocks that hold real rows
-        const int m_last = (int)((H - 1) >> 5);             // last output block
+        const int n_blk_in = (int)((H + RB - 1) / RB);      // field blocks that hold real rows
+        const int m_last = (int)((H - 1) / RB);             // last output block
 
         if (is_loader) {
             // ===================================== LOADER ===========================================
@@ -165,10 +169,10 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             const long long cs0 = SL.xs0, cs1 = SL.xs0 + SL.ncols;  // stored columns
 
             auto load_block = [&](int n) {
-                // rows [32n, 32n+32) of columns q0.. (u: q0+1..) -> slot n % NS_IN
+                // rows [RB*n, RB*n + RB) of columns q0.. (u: q0+1..) -> slot n % NS_IN
                 const int slot = n % NS_IN;
                 mbar_wait(&sm.in_empty[slot], ((n / NS_IN) & 1) ^ 1);
-                int need = 32 * n + 32;
+                int need = RB * n + RB;
                 if (need > (int)H) need = (int)H;
                 if (known_rows < need) {
                     do {
@@ -179,18 +183,20 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     if (SL.multi) fence_sys(); else fence_gpu();  // acquire
                 }
                 if (n < n_blk_in) {
-                    const long long row0 = 32LL * n;
-                    const int part = lane & 7;  // 16-byte piece of the column's 128-byte line
+                    const long long row0 = (long long)RB * n;
+                    constexpr int PPC = RB / 4;            // 16-byte pieces per column
+                    constexpr int CPI = 32 / PPC;          // columns per iteration
+                    const int part = lane % PPC;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int cc = it * 4 + (lane >> 3);
+                    for (int it = 0; it < 32 / CPI; ++it) {
+                        const int cc = it * CPI + lane / PPC;
                         const long long col = q0 + cc;
                         if (col + 1 >= 0 && col + 1 < W && col + 1 >= cs0 && col + 1 < cs1)
-                            cp_async16_cg(&sm.in_u[cc][slot * 32 + part * 4], bu + (col + 1) * H + row0 + part * 4);
+                            cp_async16_cg(&sm.in_u[cc][slot * RB + part * 4], bu + (col + 1) * H + row0 + part * 4);
                         if (col >= 0 && col < W && col >= cs0 && col < cs1) {
-                            cp_async16_cg(&sm.in_v[cc][slot * 32 + part * 4], bv + col * H + row0 + part * 4);
-                            if (!first_pass) cp_async16_cg(&sm.in_p[cc][slot * 32 + part * 4], bp + col * H + row0 + part * 4);
-                            cp_async4(&sm.in_f[cc][slot * 32 + part * 4], bf + col * H + row0 + part * 4);  // static data: L1 is fine
+                            cp_async16_cg(&sm.in_v[cc][slot * RB + part * 4], bv + col * H + row0 + part * 4);
+                            if (!first_pass) cp_async16_cg(&sm.in_p[cc][slot * RB + part * 4], bp + col * H + row0 + part * 4);
+                            cp_async4(&sm.in_f[cc][slot * RB + part * 4], bf + col * H + row0 + part * 4);  // static data: L1 is fine
                         }
                     }
                 }
@@ -221,15 +227,15 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 mbar_arrive_on_cp_async(&sm.rec_full[slot]);
             };
 
-            const int n_blk_needed = ((T - 1) >> 5) + 1;  // blocks the compute warps will wait for
+            const int n_blk_needed = (T - 1) / RB + 1;  // blocks the compute warps will wait for
             TFS_TR_DECL
             load_block(0);
             TFS_TR(0)
             for (int j = 0; j < n_int; ++j) {
                 load_records(j);
                 TFS_TR(1)
-                if ((j * G) % 32 == 0) {
-                    const int n = (j * G) / 32 + 1;  // one block ahead of the compute warps
+                if ((j * G) % RB == 0) {
+                    const int n = (j * G) / RB + 1;  // one block ahead of the compute warps
                     if (n < n_blk_needed) load_block(n);
                     TFS_TR(2)
                 }
@@ -260,21 +266,22 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             const long long c_lo = SL.c_lo;
             int m_next = 0, rows_done = 0;
             // block m (rows [32m, 32m+32)) is complete once lane 31 retired its last row
-            auto done_step = [&](int m) { return min(32 * m + 62 + KB, T - 1); };
+            auto done_step = [&](int m) { return min(RB * m + (RB - 1) + 31 + KB, T - 1); };
             auto store_block = [&](int m) {
                 const int slot = m % NS_OUT;
-                const long long row0 = 32LL * m;
-                const int part = lane & 7;
+                const long long row0 = (long long)RB * m;
+                constexpr int PPC = RB / 4, CPI = 32 / PPC;
+                const int part = lane % PPC;
                 if (row0 + part * 4 < H) {  // H % 4 == 0: a float4 is entirely inside or outside the column
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int cc = it * 4 + (lane >> 3);
+                    for (int it = 0; it < 32 / CPI; ++it) {
+                        const int cc = it * CPI + lane / PPC;
                         const long long col = q0 + cc - (KB - 1);
                         if (col >= 0 && col < W) {
                             const long long idx = col * H + row0 + part * 4;
-                            const float4 vu = *reinterpret_cast<const float4 *>(&sm.out_u[cc][slot * 32 + part * 4]);
-                            const float4 vv = *reinterpret_cast<const float4 *>(&sm.out_v[cc][slot * 32 + part * 4]);
-                            const float4 vp = *reinterpret_cast<const float4 *>(&sm.out_p[cc][slot * 32 + part * 4]);
+                            const float4 vu = *reinterpret_cast<const float4 *>(&sm.out_u[cc][slot * RB + part * 4]);
+                            const float4 vv = *reinterpret_cast<const float4 *>(&sm.out_v[cc][slot * RB + part * 4]);
+                            const float4 vp = *reinterpret_cast<const float4 *>(&sm.out_p[cc][slot * RB + part * 4]);
                             if (col >= c_lo) {
                                 *reinterpret_cast<float4 *>(lu + idx) = vu;
                                 *reinterpret_cast<float4 *>(lv + idx) = vv;
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                     st_volatile64(my_prog, prog_make(seq, recs));
                     if (peer_prog) st_volatile64(peer_prog, prog_make(seq, recs));
                     if (m_next != m_first) {
-                        rows_done = min(32 * m_next, (int)H);
+                        rows_done = min(RB * m_next, (int)H);
                         st_volatile64(my_out_prog, prog_make(seq, rows_done));
                         if (peer_out_prog) st_volatile64(peer_out_prog, prog_make(seq, rows_done));
                     }
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
             // k = 0 operands of step tau: u[q+1, rho], p[q, rho], flags[q, rho], v[q, rho+1], flags[q, rho+1]
             // with rho = tau - lane - 1, read from the row rings (k-group 0 only).  rr / rr1 are this
             // lane's ring positions of rho / rho + 1 and advance by one per step.
-            constexpr int RIN = 32 * NS_IN, ROUT = 32 * NS_OUT;
+            constexpr int RIN = SM::RIN, ROUT = SM::ROUT;
             const int Hi = (int)H;
             int rr = ((-lane - 1) % RIN + RIN) % RIN;      // rho at tau = 0
             int rr1 = (rr + 1 == RIN) ? 0 : rr + 1;
@@ -371,13 +378,13 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 pin[0] = (!first_pass && col_ok && row_ok) ? o.sp : 0.0f;
                 fl = (fl & ~0xFu) | (f0 & 15u);
             };
-            // input blocks: block n is first touched (by lane 0, row rho+1 = 32n) when preparing step 32n;
-            // block n-2 is then behind lane 31 and goes back to the loader
+            // input blocks: block n is first touched (by lane 0, row rho+1 = RB*n) when preparing step RB*n;
+            // rows in use are [tau-32, tau], so block n-(NS_IN-1) is then behind lane 31 and goes back to the loader
             int in_slot = 0, in_par = 0, in_n = 0;         // next block to acquire
             int rel_slot = 0;                              // slot of block in_n - 2
             auto acquire_in_block = [&]() {
                 mbar_wait(&sm.in_full[in_slot], in_par);
-                if (in_n >= 2) {
+                if (in_n >= NS_IN - 1) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.in_empty[rel_slot]);
                     rel_slot = (rel_slot + 1 == NS_IN) ? 0 : rel_slot + 1;
@@ -407,9 +414,9 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 if (sg == 0) {
                     mbar_wait(&sm.rec_full[rec_slot], rec_par);
                     if (g == NW - 1) {
-                        // lane 0 first touches output block m at step 32m + KB: if that falls in this
+                        // lane 0 first touches output block m at step RB*m + KB: if that falls in this
                         // interval and the slot was used before, the storer must have emptied it
-                        const int first = 32 * out_m + KB;
+                        const int first = RB * out_m + KB;
                         if (first < t + G) {
                             mbar_wait(&sm.out_empty[out_slot], out_par);
                             ++out_m;
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(32 * (NW + 2)) k_project_systolic4(Sys4Params 
                 const bool have_next = (g == 0) && (t + 1 < T);
                 K0 nk0 = {0.f, 0.f, 0.f, 0u, 0u};
                 if (have_next) {
-                    if (((t + 1) & 31) == 0) acquire_in_block();
+                    if (((t + 1) % RB) == 0) acquire_in_block();
                     nk0 = load_k0();
                     advance_ring();
                 }
@@ -584,7 +591,7 @@ struct Systolic4Workspace {
     long long seq = 0;
 };
 
-template <int KG, int NW, int G>
+template <int KG, int NW, int G, int RB>
 struct Sys4Launch {
     static constexpr int KB = KG * NW;
     static cudaError_t run(const SystolicArgs &a, const Sys4External *ext, SystolicWorkspace &ws, Systolic4Workspace &ws4,
@@ -707,8 +714,8 @@ struct Sys4Launch {
         }
         P4.tasks = ws4.d_tasks;
         P4.n_tasks = (int)n_tasks;
-        auto kern = k_project_systolic4<KG, NW, G>;
-        const size_t smem = sizeof(Sys4Smem<KG, NW, G>) + 128;
+        auto kern = k_project_systolic4<KG, NW, G, RB>;
+        const size_t smem = sizeof(Sys4Smem<KG, NW, G, RB>) + 128;
         static bool attr_set[64] = {false};  // function attributes are per device
         static int occ_dev[64] = {0};
         const int di = dev & 63;
@@ -781,12 +788,14 @@ inline cudaError_t systolic_project_auto(const SystolicArgs &a, const Sys4Extern
         return systolic_project(a, ws, launched, msg);
     }
     const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
-    const char *env_g = getenv("TFS_SYS_G");
+    const char *env_g = getenv("TFS_SYS_G"), *env_rb = getenv("TFS_SYS_RB");
     const int G_ = env_g ? atoi(env_g) : 8;
+    const int RB_ = env_rb ? atoi(env_rb) : 16;
 #define TFS_SYS4_CASE(KG_, NW_)                                                                          \
     if (sh.kg == KG_ && sh.nw == NW_) {                                                                  \
-        if (G_ == 4) return Sys4Launch<KG_, NW_, 4>::run(a, ext, ws, ws4, launched, msg);                \
-        return Sys4Launch<KG_, NW_, 8>::run(a, ext, ws, ws4, launched, msg);                             \
+        if (RB_ == 16 && G_ != 4) return Sys4Launch<KG_, NW_, 8, 16>::run(a, ext, ws, ws4, launched, msg);   \
+        if (G_ == 4) return Sys4Launch<KG_, NW_, 4, 32>::run(a, ext, ws, ws4, launched, msg);            \
+        return Sys4Launch<KG_, NW_, 8, 32>::run(a, ext, ws, ws4, launched, msg);                         \
     }
     TFS_SYS4_CASE(6, 4)
     TFS_SYS4_CASE(4, 8)
@@ -800,7 +809,7 @@ inline cudaError_t systolic_project_auto(const SystolicArgs &a, const Sys4Extern
     TFS_SYS4_CASE(8, 4)
     TFS_SYS4_CASE(8, 1)
 #undef TFS_SYS4_CASE
-    if (ext) return Sys4Launch<4, 4, 8>::run(a, ext, ws, ws4, launched, msg);
+    if (ext) return Sys4Launch<4, 4, 8, 32>::run(a, ext, ws, ws4, launched, msg);
     return systolic_project(a, ws, launched, msg);
 }
 
