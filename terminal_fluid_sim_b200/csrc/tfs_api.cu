@@ -747,6 +747,7 @@ int tfs_resize(tfs_sim *s, size_t width, size_t height) {
     s->launches++;
     s->W = width;
     s->H = height;
+    s->c_lo = 0; s->c_hi = (long long)width; s->xs0 = 0; s->ncols = (long long)width;  // single-GPU handle: the slab is the grid
     rc = alloc_fields(s, n_new);  // zero-fills m
     if (rc) {
         cudaFree(m_old);
