@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
         const int tb = tk.x, b = tk.y, lb = tk.y - SL.b0;  // pass, global band, local band
         const int par = tb & 1;
         const bool last_local = lb == SL.nb_local - 1;
+        // only the bands at a slab edge talk to another GPU: everything else keeps the cheaper gpu-scope fences
+        const bool sysfence = SL.multi && (lb == 0 || last_local);
         const int k_act = (tb == P.n_passes - 1) ? P.k_last : KB;
         const bool first_pass = tb == 0;
         const long long q0 = (long long)b * 32 - 1;  // skewed coordinate of lane 0
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                         if (lane == 0) k0 = min(prog_of(ld_volatile64(dep_out0), seq), prog_of(ld_volatile64(dep_out1), seq));
                         known_rows = __shfl_sync(0xffffffffu, k0, 0);
                     } while (known_rows < need);
-                    if (SL.multi) fence_sys(); else fence_gpu();  // acquire
+                    if (sysfence) fence_sys(); else fence_gpu();  // acquire
                 }
                 if (n < n_blk_in) {
                     const long long row0 = (long long)RB * n;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                             if (lane == 0) k0 = prog_of(ld_volatile64(left_prog), seq);
                             known_left = __shfl_sync(0xffffffffu, k0, 0);
                         } while (known_left < need);
-                        if (SL.multi) fence_sys(); else fence_gpu();  // acquire
+                        if (sysfence) fence_sys(); else fence_gpu();  // acquire
                     }
                     float4 *dst = &sm.rec[slot][0][0][0];
                     for (int e = lane; e < NW * G * KG; e += 32) {
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                 while (m_next <= m_last && done_step(m_next) <= t_done) { store_block(m_next); ++m_next; }
                 __syncwarp();
                 TFS_TR(2)
-                if (SL.multi) fence_sys(); else fence_gpu();  // release: block stores above + the records the compute warps wrote
+                if (sysfence) fence_sys(); else fence_gpu();  // release: block stores above + the records the compute warps wrote
                 TFS_TR(3)
                 if (lane == 0) {
                     int recs = t_done - 32 + 1;
