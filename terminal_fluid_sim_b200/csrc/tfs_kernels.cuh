@@ -289,6 +289,22 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
                   fmul(fmul(sx, ty), f01), one);   // :294-297
 }
 
+// sample_vector for a point with 1 <= x < W-1 and 1 <= y < H-1: none of the clamps of simulator.rs:271-288
+// can bind (x, y in range; xl + 1 <= W-1; yb + 1 <= H-1), so they are not issued.  Bit-identical to
+// sample_field32 on that domain; the caller checks the domain with a warp vote.
+template <int FT>
+TFS_DEVINL float sample_interior32(const float *__restrict__ f, float x, float y, int H, float one) {
+    const float xs = (FT == FT_U) ? x : fsub_f(x, 0.5f, one), ys = (FT == FT_V) ? y : fsub_f(y, 0.5f, one);
+    const unsigned xl = __float2uint_rz(xs), yb = __float2uint_rz(ys);
+    const float tx = fsub_f(xs, (float)xl, one), ty = fsub_f(ys, (float)yb, one);
+    const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);
+    const float *p0 = f + (xl * (unsigned)H + yb);  // (xl, yb); the other three corners are +H, +H+1, +1
+    const float *p1 = p0 + H;
+    const float f00 = __ldg(p0), f10 = __ldg(p1), f11 = __ldg(p1 + 1), f01 = __ldg(p0 + 1);
+    return fadd_f(fadd_f(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11), one),
+                  fmul(fmul(sx, ty), f01), one);   // :294-297
+}
+
 // blockDim.x threads along y (rows y0 .. y0+blockDim.x), CPB columns per block marched in +x so the
 // column i+1 values loaded for cell (i, j) are reused as "own" values of cell (i+1, j).
 // SLAB: all pointers are global-column bases, only columns [c_begin, c_end) are advected, the
@@ -302,7 +318,7 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = c_begin + blockIdx.y * CPB;
     if (j >= H) return;
-    const float Wf = (float)W, Hf = (float)H;
+    const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
     const float fj = (float)j, fjh = fadd(fj, 0.5f);
     const int jm = j > 0 ? j - 1 : 0, jp = j < H - 1 ? j + 1 : j;   // clamped only for memory safety (border rows never use them)
     unsigned idx = (unsigned)i0 * (unsigned)H + (unsigned)j;
@@ -320,27 +336,32 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
         const float sC = s[idx];
         const unsigned f = flags[idx];
         float un = uC, vn = vC, sn = sC;
-        if (f & TFS_F_LIVE) {
-            const float fi = (float)i;
-            // u component (:207-213), avg_vertical (:245-255): ((((0+a)+b)+c)+d)*0.25
-            // (the leading "0 +" of Iterator::sum only affects the sign of a zero sum, which is then scaled
-            //  and subtracted from a coordinate >= 1: it cannot reach the result, so it is not issued)
-            const float avg_v = fmul(fadd_f(fadd(fadd(vL, vLT), vT), vC, one), 0.25f);
-            float xp = fsub_f(fi, fmul(uC, dt), one);
-            float yp = fsub_f(fjh, fmul(avg_v, dt), one);
-            un = sample_field32<FT_U, SLAB>(u, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
-            // v component (:216-224), avg_horizontal (:257-267)
-            const float avg_u = fmul(fadd_f(fadd(fadd(uB, uRB), uR), uC, one), 0.25f);
-            const float fih = fadd(fi, 0.5f);
-            xp = fsub_f(fih, fmul(avg_u, dt), one);
-            yp = fsub_f(fj, fmul(vC, dt), one);
-            vn = sample_field32<FT_V, SLAB>(v, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
-            // smoke (:227-237)
-            const float cv = fmul(fadd(vC, vT), 0.5f);
-            const float cu = fmul(fadd(uC, uR), 0.5f);
-            xp = fsub_f(fih, fmul(cu, dt), one);
-            yp = fsub_f(fjh, fmul(cv, dt), one);
-            sn = sample_field32<FT_S, SLAB>(s, xp, yp, W, H, Wf, Hf, one, cs0, cs1, oob);
+        const bool live = (f & TFS_F_LIVE) != 0u;
+        const float fi = (float)i, fih = fadd(fi, 0.5f);
+        // back-traced positions of the three samples (:207-236).  (The leading "0 +" of Iterator::sum only
+        // affects the sign of a zero sum, which is then scaled and subtracted from a coordinate >= 1: it
+        // cannot reach the result, so it is not issued.)
+        const float avg_v = fmul(fadd_f(fadd(fadd(vL, vLT), vT), vC, one), 0.25f);    // :245-255
+        const float avg_u = fmul(fadd_f(fadd(fadd(uB, uRB), uR), uC, one), 0.25f);    // :257-267
+        const float cv = fmul(fadd(vC, vT), 0.5f), cu = fmul(fadd(uC, uR), 0.5f);     // :228-233
+        const float xu = fsub_f(fi, fmul(uC, dt), one), yu = fsub_f(fjh, fmul(avg_v, dt), one);
+        const float xv = fsub_f(fih, fmul(avg_u, dt), one), yv = fsub_f(fj, fmul(vC, dt), one);
+        const float xsm = fsub_f(fih, fmul(cu, dt), one), ysm = fsub_f(fjh, fmul(cv, dt), one);
+        // all three points strictly inside [1, W-1) x [1, H-1)?  (NaNs fail the test and take the general path)
+        const float xmin = fminf(fminf(xu, xv), xsm), xmax = fmaxf(fmaxf(xu, xv), xsm);
+        const float ymin = fminf(fminf(yu, yv), ysm), ymax = fmaxf(fmaxf(yu, yv), ysm);
+        const bool inside = !SLAB && xmin >= 1.0f && xmax < Wm1 && ymin >= 1.0f && ymax < Hm1 &&
+                            xu == xu && xv == xv && xsm == xsm && yu == yu && yv == yv && ysm == ysm;
+        if (__all_sync(__activemask(), inside || !live)) {
+            if (live) {
+                un = sample_interior32<FT_U>(u, xu, yu, H, one);
+                vn = sample_interior32<FT_V>(v, xv, yv, H, one);
+                sn = sample_interior32<FT_S>(s, xsm, ysm, H, one);
+            }
+        } else if (live) {
+            un = sample_field32<FT_U, SLAB>(u, xu, yu, W, H, Wf, Hf, one, cs0, cs1, oob);
+            vn = sample_field32<FT_V, SLAB>(v, xv, yv, W, H, Wf, Hf, one, cs0, cs1, oob);
+            sn = sample_field32<FT_S, SLAB>(s, xsm, ysm, W, H, Wf, Hf, one, cs0, cs1, oob);
         }
         nu[idx] = un; nv[idx] = vn; ns[idx] = sn;
         // march: column i+1 becomes the own column, column i the left one
