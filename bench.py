@@ -223,6 +223,7 @@ def run_ours(args):
         pj, ad = ph3["project_ms"] / ph3["steps"], ph3["advect_ms"] / ph3["steps"]
         extra["config3_4096"] = {
             "workload": w3["name"], "value": round(c3 * 10 / (ms3 / 1e3) / 1e9, 4), "unit": "Gcell-steps/s",
+            "ncu_dram_bytes_per_projection_launch": 1.90e9, "ncu_source": "profiles/r01_systolic4_c3_4096_K100.txt",
             "ms_per_step": round(ms3 / 10, 4),
             "project": {"ms": round(pj, 4), "achieved_gbs": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9, 1),
                         "frac": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9 / peak, 4)},

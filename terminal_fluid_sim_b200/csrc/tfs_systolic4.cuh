@@ -33,11 +33,15 @@ TFS_DEVINL void mbar_arrive(unsigned long long *b) {
 TFS_DEVINL void mbar_arrive_on_cp_async(unsigned long long *b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(b)) : "memory");
 }
+// Blocking wait on phase `parity`.  `hint_ns` is the suspend-time hint of try_wait: a waiting warp sleeps in
+// hardware instead of re-issuing the poll (ncu showed ~100 spin instructions per step competing with the
+// compute warps for issue slots before this was added).
+template <unsigned HINT_NS = 400>
 TFS_DEVINL void mbar_wait(unsigned long long *b, unsigned parity) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" ::"r"(
+        "{\n\t.reg .pred p;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" ::"r"(
             smem_u32(b)),
-        "r"(parity)
+        "r"(parity), "r"(HINT_NS)
         : "memory");
 }
 
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
             auto load_block = [&](int n) {
                 // rows [RB*n, RB*n + RB) of columns q0.. (u: q0+1..) -> slot n % NS_IN
                 const int slot = n % NS_IN;
-                mbar_wait(&sm.in_empty[slot], ((n / NS_IN) & 1) ^ 1);
+                mbar_wait<4000>(&sm.in_empty[slot], ((n / NS_IN) & 1) ^ 1);
                 int need = RB * n + RB;
                 if (need > (int)H) need = (int)H;
                 if (known_rows < need) {
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                         int k0 = 0;
                         if (lane == 0) k0 = min(prog_of(ld_volatile64(dep_out0), seq), prog_of(ld_volatile64(dep_out1), seq));
                         known_rows = __shfl_sync(0xffffffffu, k0, 0);
+                        if (known_rows < need) __nanosleep(500);
                     } while (known_rows < need);
                     if (sysfence) fence_sys(); else fence_gpu();  // acquire
                 }
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
             };
             auto load_records = [&](int j) {
                 const int slot = j % NR;
-                mbar_wait(&sm.rec_empty[slot], ((j / NR) & 1) ^ 1);
+                mbar_wait<2000>(&sm.rec_empty[slot], ((j / NR) & 1) ^ 1);
                 if (has_left) {
                     int need = (j + 1) * G;
                     if (need > P.n_rec) need = P.n_rec;
@@ -215,17 +220,23 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                             int k0 = 0;
                             if (lane == 0) k0 = prog_of(ld_volatile64(left_prog), seq);
                             known_left = __shfl_sync(0xffffffffu, k0, 0);
+                            if (known_left < need) __nanosleep(300);
                         } while (known_left < need);
                         if (sysfence) fence_sys(); else fence_gpu();  // acquire
                     }
                     float4 *dst = &sm.rec[slot][0][0][0];
                     for (int e = lane; e < NW * G * KG; e += 32) {
                         const int gg = e / (G * KG), x = e % (G * KG);
-                        long long r4 = (long long)j * G * KG + x;  // float4 index inside the group's stream
-                        if (r4 >= (long long)rec_stride) r4 = (long long)rec_stride - 1;  // past the end: masked at use
-                        cp_async16_cg(dst + e, rec_in + (size_t)gg * rec_stride + r4);
+                        const long long r4 = (long long)j * G * KG + x;  // float4 index inside the group's stream
+                        if (r4 < (long long)rec_stride) cp_async16_cg(dst + e, rec_in + (size_t)gg * rec_stride + r4);
+                        else dst[e] = make_float4(0.f, 0.f, 0.f, 0.f);  // past the stream: "lane -1" produces zeros
                     }
+                } else {
+                    float4 *dst = &sm.rec[slot][0][0][0];
+                    for (int e = lane; e < NW * G * KG; e += 32) dst[e] = make_float4(0.f, 0.f, 0.f, 0.f);  // no left band
                 }
+                __threadfence_block();  // the plain zero stores above must be visible before the slot is handed over
+                __syncwarp();
                 mbar_arrive_on_cp_async(&sm.rec_full[slot]);
             };
 
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
             TFS_TR_DECL
             for (int j = 0; j < n_int; ++j) {
                 TFS_TR(0)
-                mbar_wait(&sm.rec_written[j % NPH], (j / NPH) & 1);  // steps < (j+1)*G retired by every k-group
+                mbar_wait<2000>(&sm.rec_written[j % NPH], (j / NPH) & 1);  // steps < (j+1)*G retired by every k-group
                 TFS_TR(1)
                 const int t_done = min((j + 1) * G, T) - 1;
                 int m_first = m_next;
@@ -427,8 +438,6 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                     }
                 }
                 TFS_TR(6)
-                const bool use_left = has_left && t < P.n_rec;
-                const bool patch = use_left && lane == 0;
                 // ---- early loads: left band's record (for lane 0) and next step's k = 0 operands
                 float4 lr[KG];
                 {
@@ -483,12 +492,12 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                 }
                 unsigned s_flv = __shfl_up_sync(0xffffffffu, fl_used, 1);
 #pragma unroll
-                for (int kk = 0; kk < KG; ++kk) {
-                    n_uL[kk] = (lane == 0) ? (patch ? lr[kk].x : 0.0f) : n_uL[kk];
-                    s_v[kk] = (lane == 0) ? (patch ? lr[kk].y : 0.0f) : s_v[kk];
-                    s_p[kk] = (lane == 0) ? (patch ? lr[kk].z : 0.0f) : s_p[kk];
+                for (int kk = 0; kk < KG; ++kk) {  // (the loader zero-fills the record slot where there is no left band)
+                    n_uL[kk] = (lane == 0) ? lr[kk].x : n_uL[kk];
+                    s_v[kk] = (lane == 0) ? lr[kk].y : s_v[kk];
+                    s_p[kk] = (lane == 0) ? lr[kk].z : s_p[kk];
                 }
-                s_flv = (lane == 0) ? (patch ? __float_as_uint(lr[0].w) : 0u) : s_flv;
+                s_flv = (lane == 0) ? __float_as_uint(lr[0].w) : s_flv;
                 TFS_TR(3)
                 // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
                 sm.grp[t & 1][g][lane] =
