@@ -58,7 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
-        sys.stderr.write(log)
+        err = [l for l in log.splitlines() if 'error' in l.lower()]
+        sys.stderr.write('\n'.join(err[-20:] or log.splitlines()[-20:]) + '\n')
         raise RuntimeError("nvcc failed building libtfs_cuda.so")
     if verbose:
         print(log)
