@@ -70,6 +70,13 @@ public:
     void set_block(size_t x, size_t y) { edit_block(x, y, 1); }                                                // :331
     void unset_block(size_t x, size_t y) { edit_block(x, y, 0); }                                              // :337
 
+    // additive: the renderer's colour loop (src/ui/sim_renderer.rs:23-151) on the device; cells =
+    // area_h*area_w*8 bytes, {r,g,b,kind} background then foreground per terminal cell (see tfs.h)
+    void render_view(size_t area_w, size_t area_h, std::vector<uint8_t> &cells) {
+        cells.resize(area_w * area_h * 8);
+        check(tfs_render_view(h_, 0, area_w, area_h, nullptr, cells.data(), nullptr, nullptr));
+    }
+
     tfs_sim *handle() { return h_; }  // additive: options, views, timing via the C ABI
 
 private:

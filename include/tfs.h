@@ -128,6 +128,19 @@ int tfs_write_field(tfs_sim *sim, int field, const void *src, size_t n);
 
 /* min / max of pressure_grid with the renderer's rule (src/ui/sim_renderer.rs:31-37) */
 int tfs_pressure_minmax(tfs_sim *sim, float *min_p, float *max_p);
+/* The renderer's colour loop (render_sim / render_cell / get_color / get_linear_gradient,
+ * src/ui/sim_renderer.rs:23-151) evaluated on the device for the terminal area area_w x area_h
+ * whose left edge shows sim column x0 (the reference always uses x0 = 0): terminal cell (x, row)
+ * covers the sim cells (x0+x, H-1-2*row) (background) and (x0+x, H-2-2*row) (foreground,
+ * sim_renderer.rs:45-82).  dst receives area_h*area_w cells, row-major (index = row*area_w + x,
+ * ratatui's Buffer order), 8 bytes each: {r, g, b, kind} of the background then of the
+ * foreground; kind = 0 -> Color::Rgb(r, g, b), kind = 1 -> THEME.sim_blocks (Color::White,
+ * theme.rs).  minmax_in = NULL takes min/max of the whole pressure grid as sim_renderer.rs:31-37
+ * does; an x-slab handle must pass the global {min, max}.  min_p / max_p (nullable) return the
+ * pair used.  Needs area_w <= width - x0 and 2*area_h <= height (the reference panics beyond);
+ * synchronises.  The per-frame D2H is 8 B per terminal cell. */
+int tfs_render_view(tfs_sim *sim, size_t x0, size_t area_w, size_t area_h, const float *minmax_in, void *dst, float *min_p,
+                    float *max_p);
 /* max |((u[right]-u[idx]) + v[top]) - v[idx]| over updatable cells with a fluid neighbour */
 int tfs_divergence_linf(tfs_sim *sim, float *out);
 

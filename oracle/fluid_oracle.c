@@ -414,6 +414,71 @@ void orc_fill_random_velocity(orc_sim *o, uint64_t seed, float amp) {
     }
 }
 
+/* ---- renderer colour path: src/ui/sim_renderer.rs:23-151 -------------------- */
+
+/* Rust `f32 as u8`: saturating, NaN -> 0 */
+static uint8_t f32_as_u8(float x) {
+    if (!(x > 0.0f)) return 0;
+    if (x >= 255.0f) return 255;
+    return (uint8_t)x;
+}
+
+/* get_linear_gradient (sim_renderer.rs:116-140) */
+static void linear_gradient(float value, float min, float max, uint8_t rgb[3]) {
+    float difference = max - min;
+    float normalized = (difference == 0.0f) ? 0.5f : (value - min) / difference;
+    float color_type = floorf(normalized * 4.0f);
+    float color_value = (normalized - color_type * 0.25f) / 0.25f;
+    float r, g, b;
+    switch (f32_as_u8(color_type)) {
+    case 0: r = 0.0f; g = color_value; b = 1.0f; break;
+    case 1: r = 0.0f; g = 1.0f; b = 1.0f - color_value; break;
+    case 2: r = color_value; g = 1.0f; b = 0.0f; break;
+    case 3: r = 1.0f; g = 1.0f - color_value; b = 0.0f; break;
+    default: r = 1.0f; g = 0.0f; b = 0.0f; break;
+    }
+    rgb[0] = f32_as_u8(255.0f * r);
+    rgb[1] = f32_as_u8(255.0f * g);
+    rgb[2] = f32_as_u8(255.0f * b);
+}
+
+/* render_cell + get_color (sim_renderer.rs:85-114, :142-151): out = {r, g, b, kind}; kind 1 = block
+ * (THEME.sim_blocks = Color::White, a named colour, not an RGB triple) */
+static void cell_colour(const orc_sim *o, size_t idx, float min_p, float max_p, uint8_t out[4]) {
+    if (o->m[idx]) { out[0] = out[1] = out[2] = 255; out[3] = 1; return; }
+    uint8_t rgb[3];
+    linear_gradient(o->p[idx], min_p, max_p, rgb);
+    uint8_t red = f32_as_u8(255.0f * o->s[idx]);
+    for (int c = 0; c < 3; ++c) out[c] = rgb[c] > red ? (uint8_t)(rgb[c] - red) : 0; /* saturating_sub */
+    out[3] = 0;
+}
+
+/* render_sim (sim_renderer.rs:23-83): the literal sequential min/max scan (:31-37) followed by the
+ * half-block loop.  out[(row*area_w + x)*8 + 0..3] = background (sim cell (x, H-1-2*row)),
+ * +4..7 = foreground (sim cell (x, H-2-2*row)).  Returns 1 where the reference would panic. */
+int orc_render_view(const orc_sim *o, size_t area_w, size_t area_h, uint8_t *out, float *min_out, float *max_out) {
+    const size_t W = o->width, H = o->height, n = W * H;
+    if (area_w > W || 2 * area_h > H) return 1;
+    float max_p = -3.402823466e38f, min_p = 3.402823466e38f; /* f32::MIN, f32::MAX */
+    for (size_t i = 0; i < n; ++i) {
+        float v = o->p[i];
+        if (v < min_p) min_p = v;
+        else if (v > max_p) max_p = v;
+    }
+    for (size_t x = 0; x < area_w; ++x) {
+        size_t y_index = H;
+        for (size_t row = 0; row < area_h; ++row) {
+            y_index -= 1;
+            cell_colour(o, x * H + y_index, min_p, max_p, out + (row * area_w + x) * 8);
+            y_index -= 1;
+            cell_colour(o, x * H + y_index, min_p, max_p, out + (row * area_w + x) * 8 + 4);
+        }
+    }
+    *min_out = min_p;
+    *max_out = max_p;
+    return 0;
+}
+
 /* accessors for the ctypes harness */
 float *orc_u(orc_sim *o) { return o->u; }
 float *orc_v(orc_sim *o) { return o->v; }

@@ -210,3 +210,44 @@ class NpSim:
         self.add_gravity(dt)
         self.make_incompressible(dt, lexicographic=lexicographic)
         self.move_velocity(dt)
+
+
+def _as_u8(x):
+    """Rust `f32 as u8` (saturating, NaN -> 0), vectorised"""
+    x = np.asarray(x, np.float32)
+    with np.errstate(invalid="ignore"):
+        y = np.where(x > 0, np.minimum(x, F(255.0)), F(0.0))
+    return np.trunc(y).astype(np.uint8)
+
+
+def render_view(p, s, m, W, H, area_w, area_h):
+    """Independent restatement of render_sim / get_color / get_linear_gradient
+    (src/ui/sim_renderer.rs:23-151) on float32 arrays; returns (bytes[area_h, area_w, 2, 4], min, max)."""
+    p = np.asarray(p, F); s = np.asarray(s, F)
+    mx, mn = F(-3.402823466e38), F(3.402823466e38)
+    for v in p:                                   # the literal `if < min {..} else if > max {..}` scan (:31-37)
+        if v < mn:
+            mn = v
+        elif v > mx:
+            mx = v
+    out = np.zeros((area_h, area_w, 2, 4), np.uint8)
+    rows = np.arange(area_h)
+    for half, yy in ((0, H - 1 - 2 * rows), (1, H - 2 - 2 * rows)):
+        idx = (np.arange(area_w)[None, :] * H + yy[:, None])
+        val, smoke, blk = p[idx], s[idx], m[idx] != 0
+        with np.errstate(all="ignore"):
+            diff = mx - mn
+            norm = np.full(val.shape, F(0.5), F) if diff == 0 else ((val - mn) / diff).astype(F)
+            ctype = np.floor(norm * F(4.0)).astype(F)
+            cval = ((norm - ctype * F(0.25)) / F(0.25)).astype(F)
+            ct = _as_u8(ctype)
+            one, zero = np.ones_like(cval), np.zeros_like(cval)
+            r = np.select([ct == 0, ct == 1, ct == 2, ct == 3], [zero, zero, cval, one], one)
+            g = np.select([ct == 0, ct == 1, ct == 2, ct == 3], [cval, one, one, one - cval], zero)
+            b = np.select([ct == 0, ct == 1, ct == 2, ct == 3], [one, one - cval, zero, zero], zero)
+            rgb = np.stack([_as_u8(F(255.0) * r), _as_u8(F(255.0) * g), _as_u8(F(255.0) * b)], -1).astype(np.int32)
+            red = _as_u8(F(255.0) * smoke).astype(np.int32)[..., None]
+        col = np.clip(rgb - red, 0, 255).astype(np.uint8)
+        out[:, :, half, :3] = np.where(blk[..., None], 255, col)
+        out[:, :, half, 3] = blk
+    return out, float(mn), float(mx)

@@ -51,6 +51,7 @@ def lib():
         L.orc_divergence_linf.restype = f32
         L.orc_divergence_linf.argtypes = [vp]
         L.orc_cell_flags.argtypes = [vp, vp]
+        L.orc_render_view.argtypes = [vp, sz, sz, vp, C.POINTER(f32), C.POINTER(f32)]
         L.orc_scene_disc.argtypes = [vp, C.c_long, C.c_long, C.c_long]
         L.orc_scene_lattice.argtypes = [vp, C.c_long, C.c_long]
         L.orc_scene_random.argtypes = [vp, u64, u64]
@@ -164,6 +165,14 @@ class OracleSim:
         out = np.empty(self.width * self.height, np.uint8)
         self.L.orc_cell_flags(self.h, out.ctypes.data)
         return out
+
+    def render_view(self, area_w, area_h):
+        """render_sim (sim_renderer.rs:23-83): (bytes[area_h, area_w, 2, 4], min_p, max_p)"""
+        out = np.empty((area_h, area_w, 2, 4), np.uint8)
+        mn, mx = C.c_float(), C.c_float()
+        if self.L.orc_render_view(self.h, area_w, area_h, out.ctypes.data, C.byref(mn), C.byref(mx)):
+            raise IndexError("attempt to subtract with overflow")
+        return out, mn.value, mx.value
 
     # -- scenes -----------------------------------------------------------
     def scene_disc(self, cx, cy, r):

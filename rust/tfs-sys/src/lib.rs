@@ -63,6 +63,7 @@ extern "C" {
     pub fn tfs_read_field(sim: *mut tfs_sim, field: c_int, dst: *mut c_void, n: usize) -> c_int;
     pub fn tfs_write_field(sim: *mut tfs_sim, field: c_int, src: *const c_void, n: usize) -> c_int;
     pub fn tfs_pressure_minmax(sim: *mut tfs_sim, min_p: *mut f32, max_p: *mut f32) -> c_int;
+    pub fn tfs_render_view(sim: *mut tfs_sim, x0: usize, area_w: usize, area_h: usize, minmax_in: *const f32, dst: *mut c_void, min_p: *mut f32, max_p: *mut f32) -> c_int;
     pub fn tfs_divergence_linf(sim: *mut tfs_sim, out: *mut f32) -> c_int;
     pub fn tfs_scene_disc(sim: *mut tfs_sim, cx: c_long, cy: c_long, r: c_long) -> c_int;
     pub fn tfs_scene_lattice(sim: *mut tfs_sim, pitch: c_long, r: c_long) -> c_int;

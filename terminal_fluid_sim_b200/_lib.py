@@ -16,7 +16,8 @@ SYMBOLS = [
     "tfs_create", "tfs_destroy", "tfs_resize", "tfs_restart", "tfs_set_config", "tfs_get_config",
     "tfs_set_options", "tfs_get_options", "tfs_get_size", "tfs_set_block", "tfs_upload_blocks",
     "tfs_step", "tfs_phase_gravity", "tfs_phase_project", "tfs_phase_advect", "tfs_sync",
-    "tfs_read_view", "tfs_read_field", "tfs_write_field", "tfs_pressure_minmax", "tfs_divergence_linf",
+    "tfs_read_view", "tfs_read_field", "tfs_write_field", "tfs_pressure_minmax", "tfs_render_view",
+    "tfs_divergence_linf",
     "tfs_scene_disc", "tfs_scene_lattice", "tfs_scene_random", "tfs_fill_random_velocity",
     "tfs_host_alloc", "tfs_host_free", "tfs_timer_begin", "tfs_timer_end", "tfs_set_profiling",
     "tfs_get_phase_ms", "tfs_launch_count", "tfs_selftest_division", "tfs_peer_export", "tfs_peer_attach",
@@ -83,6 +84,7 @@ def load():
     L.tfs_read_field.argtypes = [vp, i32, vp, sz]
     L.tfs_write_field.argtypes = [vp, i32, vp, sz]
     L.tfs_pressure_minmax.argtypes = [vp, pf32, pf32]
+    L.tfs_render_view.argtypes = [vp, sz, sz, sz, pf32, vp, pf32, pf32]
     L.tfs_divergence_linf.argtypes = [vp, pf32]
     L.tfs_scene_disc.argtypes = [vp, C.c_long, C.c_long, C.c_long]
     L.tfs_scene_lattice.argtypes = [vp, C.c_long, C.c_long]

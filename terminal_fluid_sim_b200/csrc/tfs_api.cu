@@ -425,19 +425,38 @@ int phase_advect(tfs_sim *s, float dt) {
     tfs::Grid g = s->grid();
     const long long W = (long long)s->W, H = (long long)s->H;
     const char *adv_env = getenv("TFS_ADVECT");  // tuning aid: "vec4" / "scalar" force the generic kernels
-    const bool fits32 = W * H < (1LL << 31) - (1LL << 20);
+    // 32-bit cell indices, and W, H < 2^22 for the magic-constant floor of the fast kernels (floor_magic)
+    const bool fits32 = W * H < (1LL << 31) - (1LL << 20) && W < (1LL << 22) && H < (1LL << 22);
+    const float4 dims = make_float4((float)W, (float)H, (float)(W - 1), (float)(H - 1));
     if (s->slab()) {
         // owned columns only; pointers are rebased to global columns, halos supply the neighbours' cells
         constexpr int CPB = 8;
         const long long sh = s->xs0 * H;
         dim3 grid(blocks_for(H, 128), blocks_for(s->c_hi - s->c_lo, CPB));
         tfs::k_advect32<CPB, true><<<grid, 128, 0, s->stream>>>(s->u - sh, s->v - sh, s->s - sh, s->flags - sh, s->u2 - sh, s->v2 - sh,
-                                                                 s->s2 - sh, (int)W, (int)H, dt, 1.0f, (int)s->c_lo, (int)s->c_hi,
+                                                                 s->s2 - sh, (int)W, (int)H, dt, 1.0f, dims, (int)s->c_lo, (int)s->c_hi,
                                                                  (unsigned)s->xs0, (unsigned)(s->xs0 + s->ncols - 1), s->d_oob);
     } else if (fits32 && !adv_env) {
-        constexpr int CPB = 8;
-        dim3 grid(blocks_for(H, 128), blocks_for(W, CPB));
-        tfs::k_advect32<CPB><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W, (int)H, dt, 1.0f);
+        // Two cells per thread with packed f32x2 arithmetic when the rows tile by 256 (k_advect32_pair), else one
+        // cell per thread; both ask the L2 for their tile up front when the column segments are 16-byte aligned.
+        static const bool pair = !(getenv("TFS_ADV_PAIR") && atoi(getenv("TFS_ADV_PAIR")) == 0);   // tuning aid
+        if (pair && H % 256 == 0) {
+            constexpr int CPB = 4;
+            auto two = [](float x) { uint32_t b; memcpy(&b, &x, 4); return (tfs::f2)b | ((tfs::f2)b << 32); };
+            const tfs::F2K k{two(1.0f), two(-1.0f), two(-0.0f)};
+            dim3 grid((unsigned)(H / 256), blocks_for(W, CPB));
+            tfs::k_advect32_pair<CPB, 8, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W,
+                                                                          (int)H, two(dt), 1.0f, k);
+        } else {
+            constexpr int CPB = 8;
+            dim3 grid(blocks_for(H, 128), blocks_for(W, CPB));
+            if (H % 16 == 0)
+                tfs::k_advect32<CPB, false, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W,
+                                                                               (int)H, dt, 1.0f, dims);
+            else
+                tfs::k_advect32<CPB><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W, (int)H, dt,
+                                                                  1.0f, dims);
+        }
     } else if (H % 4 == 0 && !(adv_env && adv_env[0] == 's')) {
         tfs::k_advect<4><<<blocks_for(W * (H / 4), 256), 256, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2,
                                                                                s->s2, g, 0, W, dt);
@@ -1007,6 +1026,48 @@ int tfs_pressure_minmax(tfs_sim *s, float *min_p, float *max_p) {
     // (border cells are never written), after which the rule equals plain min/max; the only grid
     // where it differs is the single-cell one, where max stays f32::MIN.
     if (s->gn() == 1) *max_p = -3.402823466e38f;
+    return TFS_OK;
+}
+
+// render_sim's colour loop (src/ui/sim_renderer.rs:23-83) on the device.  dst receives
+// area_h*area_w terminal cells, row-major, 8 bytes each: {r,g,b,kind} of the background (sim cell
+// (x0+x, H-1-2*row)) then of the foreground (sim cell (x0+x, H-2-2*row)).
+int tfs_render_view(tfs_sim *s, size_t x0, size_t area_w, size_t area_h, const float *minmax_in, void *dst, float *min_p,
+                    float *max_p) {
+    NEED(s && dst, TFS_ERR_INVALID_ARG, "NULL argument");
+    if (x0 > s->W || area_w > s->W - x0 || area_h > s->H / 2)  // the reference's `y_index -= 1` would underflow
+        return fail(TFS_ERR_OUT_OF_RANGE, "terminal area %zu x %zu at column %zu exceeds the %zu x %zu grid", area_w, area_h, x0, s->W, s->H);
+    if ((long long)x0 < s->xs0 || (long long)(x0 + area_w) > s->xs0 + s->ncols)
+        return fail(TFS_ERR_OUT_OF_RANGE, "view columns [%zu, %zu) are not stored on this slab ([%lld, %lld))", x0, x0 + area_w, s->xs0,
+                    s->xs0 + s->ncols);
+    NEED(minmax_in || s->world == 1, TFS_ERR_INVALID_ARG, "an x-slab handle needs the global {min, max} in minmax_in");
+    int rc = set_device(s);
+    if (rc) return rc;
+    float *d_mm = s->d_part + 2 * 4096 - 2;
+    if (minmax_in) {
+        CU(cudaMemcpyAsync(d_mm, minmax_in, 2 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        const long long n = s->n();
+        const int nb = (int)std::min<long long>(blocks_for(n, 256 * 8), 2048);
+        tfs::k_minmax_partial<<<nb, 256, 0, s->stream>>>(s->p, n, s->d_part);
+        tfs::k_minmax_final<<<1, 256, 0, s->stream>>>(s->d_part, nb, d_mm);
+        s->launches += 2;
+    }
+    const size_t bytes = area_w * area_h * 8;
+    if (bytes) {
+        rc = ensure_stage(s, bytes);
+        if (rc) return rc;
+        dim3 grid((unsigned)((area_w + 31) / 32), (unsigned)((area_h + 31) / 32));
+        tfs::k_render_view<<<grid, 256, 0, s->stream>>>(s->p, s->s, s->m, s->grid(), (long long)x0, (int)area_w, (int)area_h, d_mm,
+                                                        (uint32_t *)s->d_stage);
+        s->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaMemcpyAsync(s->h_pin, d_mm, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (min_p) *min_p = s->h_pin[0];
+    if (max_p) *max_p = (s->gn() == 1 && !minmax_in) ? -3.402823466e38f : s->h_pin[1];  // see tfs_pressure_minmax
     return TFS_OK;
 }
 

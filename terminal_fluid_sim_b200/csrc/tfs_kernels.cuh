@@ -256,6 +256,16 @@ k_advect(const float *__restrict__ u, const float *__restrict__ v, const float *
 TFS_DEVINL float fadd_f(float a, float b, float one) { return __fmaf_rn(a, one, b); }
 TFS_DEVINL float fsub_f(float a, float b, float one) { return __fmaf_rn(b, -one, a); }
 
+// floor of 0 <= x < 2^22 without the conversion pipe: F2I / I2F issue at 1/8 and 1/4 of the FP32 rate
+// on sm_100 (scripts/micro/cvt_rate.cu: 8 and 4 cycles per warp instruction), and a bilinear sample needs
+// two of each.  RZ(x + 2^23) = 2^23 + floor(x) exactly (floats in [2^23, 2^24) are the integers), so the
+// integer is the low mantissa bits and the float floor is one exact subtraction.  Same values as
+// `x as usize` / `xl as f32` (simulator.rs:283-289) on that domain.
+#define TFS_MAGIC 8388608.0f
+TFS_DEVINL float floor_magic(float x) { return __fadd_rz(x, TFS_MAGIC); }                  // 2^23 + floor(x)
+TFS_DEVINL unsigned magic_uint(float y) { return __float_as_uint(y) - 0x4B000000u; }       // floor(x) as integer
+TFS_DEVINL float magic_float(float y, float one) { return __fmaf_rn(y, one, -TFS_MAGIC); }  // floor(x) as f32 (exact)
+
 // SLAB: `f` is a global-column base (storage pointer - xs0*H); columns outside the stored range
 // [cs0, cs1] are clamped for memory safety and reported through *oob (halo too small for this dt).
 template <int FT, bool SLAB = false>
@@ -266,10 +276,12 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
     x = fmaxf(fminf(x, Wf), 1.0f);                 // :271
     y = fmaxf(fminf(y, Hf), 1.0f);                 // :272
     const float xs = (FT == FT_U) ? x : fsub_f(x, dx, one), ys = (FT == FT_V) ? y : fsub_f(y, dy, one);  // x - 0.0 == x
-    const unsigned xl = min(__float2uint_rz(xs), (unsigned)(W - 1));   // :283 (xs >= 0.5: floor == trunc)
-    const float tx = fsub_f(xs, (float)xl, one);                       // :285
-    const unsigned yb = min(__float2uint_rz(ys), (unsigned)(H - 1));   // :287
-    const float ty = fsub_f(ys, (float)yb, one);                       // :289
+    // xs, ys in [0.5, 2^22): floor by the magic constant; the min(.., W-1) / min(.., H-1) clamps of :283 / :287
+    // are applied to the float image first (order-preserving), so index and fraction see the same value
+    const float xm = fminf(floor_magic(xs), TFS_MAGIC - 1.0f + Wf), ym = fminf(floor_magic(ys), TFS_MAGIC - 1.0f + Hf);   // 2^23 + (W-1), exact
+    const unsigned xl = magic_uint(xm), yb = magic_uint(ym);           // :283, :287
+    const float tx = fsub_f(xs, magic_float(xm, one), one);            // :285
+    const float ty = fsub_f(ys, magic_float(ym, one), one);            // :289
     const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);  // :291-292
     // xr = min(xl+1, W-1), yt = min(yb+1, H-1) (:284, :288) as index offsets: +H / +1 unless clamped
     unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
@@ -295,8 +307,9 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
 template <int FT>
 TFS_DEVINL float sample_interior32(const float *__restrict__ f, float x, float y, int H, float one) {
     const float xs = (FT == FT_U) ? x : fsub_f(x, 0.5f, one), ys = (FT == FT_V) ? y : fsub_f(y, 0.5f, one);
-    const unsigned xl = __float2uint_rz(xs), yb = __float2uint_rz(ys);
-    const float tx = fsub_f(xs, (float)xl, one), ty = fsub_f(ys, (float)yb, one);
+    const float xm = floor_magic(xs), ym = floor_magic(ys);
+    const unsigned xl = magic_uint(xm), yb = magic_uint(ym);
+    const float tx = fsub_f(xs, magic_float(xm, one), one), ty = fsub_f(ys, magic_float(ym, one), one);
     const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);
     const float *p0 = f + (xl * (unsigned)H + yb);  // (xl, yb); the other three corners are +H, +H+1, +1
     const float *p1 = p0 + H;
@@ -305,21 +318,50 @@ TFS_DEVINL float sample_interior32(const float *__restrict__ f, float x, float y
                   fmul(fmul(sx, ty), f01), one);   // :294-297
 }
 
+// Ask the L2 for the block's whole tile up front: rows [r0, r0 + rows) of the columns [i0, i0 + ncol]
+// of u and v, [i0, i0 + ncol) of s and flags, one bulk prefetch (cp.async.bulk.prefetch.L2, a TMA
+// operation without destination) per column and array, issued by the first 4*ncol + 2 threads.  The
+// march below otherwise exposes two dependent DRAM latencies per column with far too few bytes in
+// flight per SM to saturate HBM; with the tile already on its way the loads
+// hit the L2 instead.  Needs H % 4 == 0 and r0 % 4 == 0 (16-byte aligned column segments).
+TFS_DEVINL void prefetch_tile_l2(const float *u, const float *v, const float *s, const uint8_t *flags, int W, int H, int i0,
+                                 int ncol, int r0, int rows) {
+    const int t = threadIdx.x, nuv = ncol + 1;
+    const void *src = nullptr;
+    unsigned bytes = (unsigned)rows * 4u;
+    if (t < 2 * nuv) {
+        const int c = i0 + (t >> 1);
+        if (c < W) src = ((t & 1) ? v : u) + ((long long)c * H + r0);
+    } else if (t < 2 * nuv + 2 * ncol) {
+        const int q = t - 2 * nuv, c = i0 + (q >> 1);
+        if (c < W) {
+            if (q & 1) { src = flags + ((long long)c * H + r0); bytes = (unsigned)rows; }
+            else src = s + ((long long)c * H + r0);
+        }
+    }
+    if (src) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // blockDim.x threads along y (rows y0 .. y0+blockDim.x), CPB columns per block marched in +x so the
 // column i+1 values loaded for cell (i, j) are reused as "own" values of cell (i+1, j).
 // SLAB: all pointers are global-column bases, only columns [c_begin, c_end) are advected, the
 // stored columns are [cs0, cs1].
-template <int CPB, bool SLAB = false>
+// L2PF: see prefetch_tile_l2.
+template <int CPB, bool SLAB = false, bool L2PF = false>
 __global__ void __launch_bounds__(256)
 k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
            const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
-           float *__restrict__ ns, int W, int H, float dt, float one, int c_begin = 0, int c_end = 0x7fffffff,
+           float *__restrict__ ns, int W, int H, float dt, float one, float4 dims, int c_begin = 0, int c_end = 0x7fffffff,
            unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = c_begin + blockIdx.y * CPB;
+    if (L2PF) prefetch_tile_l2(u, v, s, flags, W, H, i0, CPB, blockIdx.x * blockDim.x, min((int)blockDim.x, H - (int)(blockIdx.x * blockDim.x)));
     if (j >= H) return;
-    const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+    // dims = {W, H, W-1, H-1} as floats, converted on the host: ptxas otherwise re-converts them every column,
+    // and I2F issues at a quarter of the FP32 rate (scripts/micro/cvt_rate.cu)
+    const float Wf = dims.x, Hf = dims.y, Wm1 = dims.z, Hm1 = dims.w;
     const float fj = (float)j, fjh = fadd(fj, 0.5f);
+    float fi = (float)i0;
     const int jm = j > 0 ? j - 1 : 0, jp = j < H - 1 ? j + 1 : j;   // clamped only for memory safety (border rows never use them)
     unsigned idx = (unsigned)i0 * (unsigned)H + (unsigned)j;
     // values of column i (own) and column i-1 (left)
@@ -337,7 +379,7 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
         const unsigned f = flags[idx];
         float un = uC, vn = vC, sn = sC;
         const bool live = (f & TFS_F_LIVE) != 0u;
-        const float fi = (float)i, fih = fadd(fi, 0.5f);
+        const float fih = fadd(fi, 0.5f);
         // back-traced positions of the three samples (:207-236).  (The leading "0 +" of Iterator::sum only
         // affects the sign of a zero sum, which is then scaled and subtracted from a coordinate >= 1: it
         // cannot reach the result, so it is not issued.)
@@ -368,6 +410,151 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
         vL = vC; vLT = vT;
         uC = uR; uB = uRB; vC = vR; vT = vRT;
         idx = idr;
+        fi = fadd_f(fi, 1.0f, one);   // == (float)(i + 1): integers below 2^24 are exact
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// move_velocity, packed variant: one thread advects TWO cells of a column (rows j and j + 128) and
+// carries every f32 quantity of the pair in one 64-bit register pair, so each arithmetic step of
+// simulator.rs:207-297 is ONE Blackwell packed instruction (FFMA2 via fma.rn.f32x2, two independent
+// IEEE round-to-nearest FMAs) for both cells.  k_advect32 is issue-bound (ncu: ~190 warp instructions
+// per cell, issue slots 72 % busy); packing halves the floating-point share of that.
+// Bit-exactness: every operation is issued as an FMA that is EXACT in its extra operand:
+//   a + b = fma(a, 1, b)      a - b = fma(b, -1, a)      a * b = fma(a, b, -0.0)
+// (a*1 and b*-1 are exact; x + (-0.0) == x for every x including both zeros).  The constants 1, -1
+// and -0.0 arrive as kernel arguments so ptxas cannot turn an FMA back into mul/add: it contracts even
+// explicitly rounded mul.rn.f32x2 + add.rn.f32x2 pairs into one FFMA2 (observed, ptxas 12.9, --fmad
+// false), which would fuse a*b+c and break parity with the reference.
+typedef unsigned long long f2;
+TFS_DEVINL f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+TFS_DEVINL float f2_lo(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
+TFS_DEVINL float f2_hi(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return hi; }
+TFS_DEVINL f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+TFS_DEVINL f2 f2_add_rz(f2 a, f2 b) { f2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+struct F2K { f2 one, mone, nzero; };  // (1, 1), (-1, -1), (-0.0, -0.0): runtime values, see above
+TFS_DEVINL f2 add2(f2 a, f2 b, const F2K &k) { return f2_fma(a, k.one, b); }
+TFS_DEVINL f2 sub2(f2 a, f2 b, const F2K &k) { return f2_fma(b, k.mone, a); }
+TFS_DEVINL f2 mul2(f2 a, f2 b, const F2K &k) { return f2_fma(a, b, k.nzero); }
+
+// sample_vector on the clamp-free interior domain (see sample_interior32) for the cell pair.  Both
+// points must be inside [1, W-1) x [1, H-1) (also for a cell that is not live, whose result the
+// caller discards), so all eight loads are unconditional.
+template <int FT>
+TFS_DEVINL f2 sample_interior_pair(const float *__restrict__ f, f2 x, f2 y, int H, const F2K &k) {
+    const f2 mhalf = f2_pack(-0.5f, -0.5f);
+    const f2 xs = (FT == FT_U) ? x : f2_fma(x, k.one, mhalf), ys = (FT == FT_V) ? y : f2_fma(y, k.one, mhalf);  // :277-281
+    const f2 magic = f2_pack(TFS_MAGIC, TFS_MAGIC), mmagic = f2_pack(-TFS_MAGIC, -TFS_MAGIC);
+    const f2 xm = f2_add_rz(xs, magic), ym = f2_add_rz(ys, magic);     // 2^23 + floor, see floor_magic
+    const unsigned xlA = (unsigned)xm - 0x4B000000u, xlB = (unsigned)(xm >> 32) - 0x4B000000u;                // :283
+    const unsigned ybA = (unsigned)ym - 0x4B000000u, ybB = (unsigned)(ym >> 32) - 0x4B000000u;                // :287
+    const f2 tx = sub2(xs, f2_fma(xm, k.one, mmagic), k), ty = sub2(ys, f2_fma(ym, k.one, mmagic), k);        // :285, :289
+    const f2 sx = f2_fma(tx, k.mone, k.one), sy = f2_fma(ty, k.mone, k.one);                                 // :291-292
+    const float *a0 = f + (xlA * (unsigned)H + ybA), *a1 = a0 + H;   // (xl, yb); the other corners are +H, +H+1, +1
+    const float *b0 = f + (xlB * (unsigned)H + ybB), *b1 = b0 + H;
+    const f2 f00 = f2_pack(__ldg(a0), __ldg(b0)), f10 = f2_pack(__ldg(a1), __ldg(b1));
+    const f2 f11 = f2_pack(__ldg(a1 + 1), __ldg(b1 + 1)), f01 = f2_pack(__ldg(a0 + 1), __ldg(b0 + 1));
+    const f2 t0 = mul2(mul2(sx, sy, k), f00, k), t1 = mul2(mul2(tx, sy, k), f10, k);
+    const f2 t2 = mul2(mul2(tx, ty, k), f11, k), t3 = mul2(mul2(sx, ty, k), f01, k);
+    return add2(add2(add2(t0, t1, k), t2, k), t3, k);   // :294-297
+}
+
+// all six floats in [lo, hi), tested on their bit patterns: for 0 < lo <= x the f32 order equals the
+// unsigned order of the bits; negatives (sign bit set) and NaNs (above +inf) exceed every hi.
+TFS_DEVINL bool in_range6(f2 a, f2 b, f2 c, unsigned lo_bits, unsigned hi_bits) {
+    const unsigned a0 = (unsigned)a, a1 = (unsigned)(a >> 32), b0 = (unsigned)b, b1 = (unsigned)(b >> 32);
+    const unsigned c0 = (unsigned)c, c1 = (unsigned)(c >> 32);
+    const unsigned mn = min(min(min(a0, b0), c0), min(min(a1, b1), c1));
+    const unsigned mx = max(max(max(a0, b0), c0), max(max(a1, b1), c1));
+    return (mn >= lo_bits) & (mx < hi_bits);
+}
+
+// the rare general path of one cell (clamps of simulator.rs:271-288 may bind), out of line to keep the
+// unrolled main loop small
+struct Uvs { float u, v, s; };
+__device__ __noinline__ Uvs advect_general32(const float *__restrict__ u, const float *__restrict__ v,
+                                             const float *__restrict__ s, int W, int H, float one, float xu, float yu,
+                                             float xv, float yv, float xsm, float ysm) {
+    const float Wf = (float)W, Hf = (float)H;
+    Uvs r;
+    r.u = sample_field32<FT_U>(u, xu, yu, W, H, Wf, Hf, one);
+    r.v = sample_field32<FT_V>(v, xv, yv, W, H, Wf, Hf, one);
+    r.s = sample_field32<FT_S>(s, xsm, ysm, W, H, Wf, Hf, one);
+    return r;
+}
+
+// 128 threads: thread t of block (bx, by) owns rows jA = 256*bx + t and jB = jA + 128 of the columns
+// [CPB*by, CPB*by + CPB), marched in +x like k_advect32.  Needs H % 256 == 0 and W*H < 2^31.
+// A warp takes the clamp-free path when all 6 x 64 back-traced coordinates of its cells lie inside
+// [1, W-1) x [1, H-1) - cells that are not live included, so the warps holding the rows 0 / H-1 and
+// the columns 0 / W-1 always take the general path (about 3 % of the warps at 4096^2).
+template <int CPB, int MINB, bool L2PF>
+__global__ void __launch_bounds__(128, MINB)
+k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
+                const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
+                float *__restrict__ ns, int W, int H, f2 dt2, float one, F2K k) {
+    constexpr int RB = 128;  // row distance of the two cells
+    const int jA = blockIdx.x * (2 * RB) + threadIdx.x, jB = jA + RB;
+    const int i0 = blockIdx.y * CPB;
+    if (L2PF) prefetch_tile_l2(u, v, s, flags, W, H, i0, CPB, blockIdx.x * (2 * RB), 2 * RB);
+    const unsigned one_bits = 0x3f800000u, wm1_bits = __float_as_uint((float)(W - 1)), hm1_bits = __float_as_uint((float)(H - 1));
+    const f2 half2 = f2_pack(0.5f, 0.5f), quarter2 = f2_pack(0.25f, 0.25f);
+    const f2 fj = f2_pack((float)jA, (float)jB), fjh = add2(fj, half2, k);
+    // row offsets of the (j-1) and (j+1) neighbours relative to row jA; clamped only for memory safety
+    const int dAm = jA > 0 ? -1 : 0, dBp = RB + (jB < H - 1 ? 1 : 0);
+    long long idx = (long long)i0 * H + jA;
+    const float *pu = u + idx, *pv = v + idx;
+    f2 uC = f2_pack(pu[0], pu[RB]), vC = f2_pack(pv[0], pv[RB]);
+    f2 uB = f2_pack(pu[dAm], pu[RB - 1]), vT = f2_pack(pv[1], pv[dBp]);
+    f2 vL = 0ull, vLT = 0ull;
+    if (i0 > 0) { vL = f2_pack(pv[-H], pv[RB - H]); vLT = f2_pack(pv[1 - H], pv[dBp - H]); }
+    f2 fi = f2_pack((float)i0, (float)i0);
+#pragma unroll
+    for (int c = 0; c < CPB; ++c) {
+        const int i = i0 + c;
+        if (i >= W) break;
+        const int hr = (i + 1 < W) ? H : 0;   // to column i+1; clamped for memory safety only
+        const float *pur = u + idx + hr, *pvr = v + idx + hr, *ps = s + idx;
+        const uint8_t *pf = flags + idx;
+        const f2 uR = f2_pack(pur[0], pur[RB]), uRB = f2_pack(pur[dAm], pur[RB - 1]);
+        const f2 vR = f2_pack(pvr[0], pvr[RB]), vRT = f2_pack(pvr[1], pvr[dBp]);
+        const float sA = ps[0], sB = ps[RB];
+        const bool liveA = (pf[0] & TFS_F_LIVE) != 0u, liveB = (pf[RB] & TFS_F_LIVE) != 0u;
+        const f2 fih = add2(fi, half2, k);
+        // back-traced positions (:207-236), same association as k_advect32
+        const f2 avg_v = mul2(add2(add2(add2(vL, vLT, k), vT, k), vC, k), quarter2, k);   // :245-255
+        const f2 avg_u = mul2(add2(add2(add2(uB, uRB, k), uR, k), uC, k), quarter2, k);   // :257-267
+        const f2 cv = mul2(add2(vC, vT, k), half2, k), cu = mul2(add2(uC, uR, k), half2, k);   // :228-233
+        const f2 xu = sub2(fi, mul2(uC, dt2, k), k), yu = sub2(fjh, mul2(avg_v, dt2, k), k);
+        const f2 xv = sub2(fih, mul2(avg_u, dt2, k), k), yv = sub2(fj, mul2(vC, dt2, k), k);
+        const f2 xsm = sub2(fih, mul2(cu, dt2, k), k), ysm = sub2(fjh, mul2(cv, dt2, k), k);
+        const bool inside = in_range6(xu, xv, xsm, one_bits, wm1_bits) & in_range6(yu, yv, ysm, one_bits, hm1_bits);
+        float unA = f2_lo(uC), unB = f2_hi(uC), vnA = f2_lo(vC), vnB = f2_hi(vC), snA = sA, snB = sB;
+        if (__all_sync(0xffffffffu, inside)) {
+            const f2 un = sample_interior_pair<FT_U>(u, xu, yu, H, k);
+            const f2 vn = sample_interior_pair<FT_V>(v, xv, yv, H, k);
+            const f2 sn = sample_interior_pair<FT_S>(s, xsm, ysm, H, k);
+            if (liveA) { unA = f2_lo(un); vnA = f2_lo(vn); snA = f2_lo(sn); }
+            if (liveB) { unB = f2_hi(un); vnB = f2_hi(vn); snB = f2_hi(sn); }
+        } else {
+            if (liveA) {
+                const Uvs r = advect_general32(u, v, s, W, H, one, f2_lo(xu), f2_lo(yu), f2_lo(xv), f2_lo(yv), f2_lo(xsm), f2_lo(ysm));
+                unA = r.u; vnA = r.v; snA = r.s;
+            }
+            if (liveB) {
+                const Uvs r = advect_general32(u, v, s, W, H, one, f2_hi(xu), f2_hi(yu), f2_hi(xv), f2_hi(yv), f2_hi(xsm), f2_hi(ysm));
+                unB = r.u; vnB = r.v; snB = r.s;
+            }
+        }
+        float *qu = nu + idx, *qv = nv + idx, *qs = ns + idx;
+        qu[0] = unA; qu[RB] = unB;
+        qv[0] = vnA; qv[RB] = vnB;
+        qs[0] = snA; qs[RB] = snB;
+        // march: column i+1 becomes the own column, column i the left one
+        vL = vC; vLT = vT;
+        uC = uR; uB = uRB; vC = vR; vT = vRT;
+        idx += hr;
+        fi = add2(fi, k.one, k);   // exact: integers below 2^24
     }
 }
 
@@ -485,6 +672,61 @@ __global__ void k_pack_view(const T *__restrict__ src, T *__restrict__ dst, Grid
     if (t >= vw * vh) return;
     long long x = vx0 + t / vh, y = vy0 + t % vh;
     dst[t] = src[(x - g.x0) * g.H + y];
+}
+
+// ---------------------------------------------------------------------------------------------
+// renderer colour path (src/ui/sim_renderer.rs:85-151) on the device: the per-frame D2H becomes
+// 8 bytes per terminal cell instead of three f32/u8 fields of the visible window.
+
+// Rust `f32 as u8`: truncating, saturating, NaN -> 0  (cvt.rzi.u32.f32 saturates and maps NaN to 0)
+TFS_DEVINL unsigned f32_as_u8(float x) { return min(__float2uint_rz(x), 255u); }
+
+// get_linear_gradient (:116-140) then get_color (:142-151) / THEME.sim_blocks (:92); returns
+// r | g<<8 | b<<16 | kind<<24, kind 1 = block (the named colour White, not an RGB triple)
+TFS_DEVINL uint32_t cell_colour(float value, float smoke, uint8_t block, float mn, float mx) {
+    if (block) return 0x01FFFFFFu;
+    const float difference = fsub(mx, mn);
+    const float normalized = (difference == 0.0f) ? 0.5f : __fdiv_rn(fsub(value, mn), difference);
+    const float color_type = floorf(fmul(normalized, 4.0f));
+    const float cv = __fdiv_rn(fsub(normalized, fmul(color_type, 0.25f)), 0.25f);
+    float r, g, b;
+    switch (f32_as_u8(color_type)) {
+    case 0: r = 0.0f; g = cv; b = 1.0f; break;
+    case 1: r = 0.0f; g = 1.0f; b = fsub(1.0f, cv); break;
+    case 2: r = cv; g = 1.0f; b = 0.0f; break;
+    case 3: r = 1.0f; g = fsub(1.0f, cv); b = 0.0f; break;
+    default: r = 1.0f; g = 0.0f; b = 0.0f; break;
+    }
+    const unsigned red = f32_as_u8(fmul(255.0f, smoke));
+    const unsigned R = f32_as_u8(fmul(255.0f, r)), G = f32_as_u8(fmul(255.0f, g)), B = f32_as_u8(fmul(255.0f, b));
+    return (R - min(R, red)) | ((G - min(G, red)) << 8) | ((B - min(B, red)) << 16);  // saturating_sub
+}
+
+// One CTA colours a tile of 32 columns x 64 sim rows (= 32 terminal rows, two cells each,
+// sim_renderer.rs:45-82): phase 1 reads p/s/m with threads along y (the contiguous direction of
+// idx = x*H + y), phase 2 writes with threads along x (the contiguous direction of the terminal
+// buffer, index = row*area_w + x; bg colour first = the UPPER sim cell H-1-2*row, then fg).
+__global__ void __launch_bounds__(256) k_render_view(const float *__restrict__ p, const float *__restrict__ s,
+                                                     const uint8_t *__restrict__ m, Grid g, long long vx0, int area_w, int area_h,
+                                                     const float *__restrict__ minmax, uint32_t *__restrict__ out) {
+    __shared__ uint32_t tile[64][33];
+    const float mn = minmax[0], mx = minmax[1];
+    const int tx0 = blockIdx.x * 32, row0 = blockIdx.y * 32;
+    for (int id = threadIdx.x; id < 32 * 64; id += 256) {
+        const int ly = id & 63, lx = id >> 6;
+        const int x = tx0 + lx, trow = row0 + (ly >> 1);
+        if (x < area_w && trow < area_h) {
+            const long long y = g.H - 1 - 2LL * row0 - ly;
+            const long long idx = (vx0 + x - g.x0) * g.H + y;
+            tile[ly][lx] = cell_colour(p[idx], s[idx], m[idx], mn, mx);
+        }
+    }
+    __syncthreads();
+    for (int id = threadIdx.x; id < 32 * 64; id += 256) {
+        const int j = id & 63, r = id >> 6;  // j = 2*lx + half within terminal row r of the tile
+        const int x = tx0 + (j >> 1), trow = row0 + r;
+        if (x < area_w && trow < area_h) out[((long long)trow * area_w + x) * 2 + (j & 1)] = tile[2 * r + (j & 1)][j >> 1];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -190,6 +190,20 @@ class FluidSim:
         check(self._L.tfs_pressure_minmax(self._h, C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def render_view(self, area_w: int, area_h: int, x0: int = 0, minmax=None, out: np.ndarray | None = None):
+        """render_sim's colour loop (src/ui/sim_renderer.rs:23-151) on the device.
+
+        Returns (cells[area_h, area_w, 2, 4] uint8, min_p, max_p): cells[row, x, 0] is the
+        background {r, g, b, kind} (sim cell (x0+x, H-1-2*row)), cells[row, x, 1] the foreground
+        (sim cell (x0+x, H-2-2*row)); kind 1 = block (Color::White), 0 = Color::Rgb."""
+        if out is None:
+            out = np.empty((area_h, area_w, 2, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.size == area_h * area_w * 8 and out.flags.c_contiguous
+        mm = None if minmax is None else (C.c_float * 2)(*minmax)
+        mn, mx = C.c_float(), C.c_float()
+        check(self._L.tfs_render_view(self._h, x0, area_w, area_h, mm, out.ctypes.data, C.byref(mn), C.byref(mx)))
+        return out, mn.value, mx.value
+
     def divergence_linf(self) -> float:
         r = C.c_float()
         check(self._L.tfs_divergence_linf(self._h, C.byref(r)))

@@ -20,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.np_oracle import NpSim  # noqa: E402
+from oracle.np_oracle import NpSim, render_view  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DT = float(np.float32(1.0 / 60.0))
@@ -113,7 +113,34 @@ def main():
         m_after_restart=s.m.copy(), u_after_restart=s.u.copy(), s_after_restart=s.s.copy(),
         **{f + "_after": a for f, a in fields_after.items()})
     print("edit_path done")
+    render_goldens()
+
+
+def render_goldens():
+    """Terminal cells (src/ui/sim_renderer.rs:23-151) of the last stored step of three cases, from
+    np_oracle.render_view; plus a synthetic field that reaches every branch of the colour map."""
+    out = {}
+    for name, aw, ah in (("term_80x48_disc", 80, 24), ("term_48x42_random_gravity", 48, 21), ("odd_37x23", 30, 11)):
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        prm = json.loads(bytes(z["params"]).decode())
+        st = max(prm["keep"])
+        cells, mn, mx = render_view(z[f"p_step{st}"], z[f"s_step{st}"], z["mask"], prm["W"], prm["H"], aw, ah)
+        out[name] = cells
+        out[name + "_minmax"] = np.array([mn, mx], np.float32)
+        out[name + "_area"] = np.array([aw, ah])
+    W, H = 40, 36
+    rng = np.random.default_rng(9)
+    p = rng.uniform(-2000, 3000, W * H).astype(np.float32)
+    p[:2] = 0
+    s = rng.uniform(-0.2, 1.2, W * H).astype(np.float32)      # outside [0, 1]: the `as u8` saturation
+    s[rng.random(W * H) < 0.5] = 0
+    m = (rng.random(W * H) < 0.1).astype(np.uint8)
+    p[5], s[6] = np.float32("nan"), np.float32("nan")
+    cells, mn, mx = render_view(p, s, m, W, H, W, H // 2)
+    out.update(synthetic=cells, synthetic_p=p, synthetic_s=s, synthetic_m=m, synthetic_minmax=np.array([mn, mx], np.float32))
+    np.savez_compressed(os.path.join(HERE, "render_view.npz"), **out)
+    print("render_view done")
 
 
 if __name__ == "__main__":
-    main()
+    render_goldens() if "--render-only" in sys.argv else main()

@@ -192,3 +192,70 @@ def test_launch_counter_moves():
     a = g.launch_count()
     g.next_step(DT); g.sync()
     assert g.launch_count() > a
+
+
+# ---- renderer colour path on the device (src/ui/sim_renderer.rs:23-151) ---------------
+@pytest.mark.parametrize("W,H,aw,ah", [(80, 48, 80, 24), (100, 100, 100, 50), (37, 23, 30, 11), (200, 150, 131, 70),
+                                       (64, 64, 10, 3), (7, 2, 7, 1), (3, 1, 3, 0)])
+def test_render_view_cells_bit_exact(W, H, aw, ah):
+    g, o = make_pair(W, H, gravity=-9.8, iterations=10)
+    rng = np.random.default_rng(W * 1000 + H)
+    for _ in range(W * H // 15):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        g.set_block(x, y); o.set_block(x, y)
+    for _ in range(3):
+        g.next_step(DT); o.step(DT)
+    want, mn, mx = o.render_view(aw, ah)
+    got, gmn, gmx = g.render_view(aw, ah)
+    assert (gmn, gmx) == (mn, mx) == g.pressure_minmax()
+    assert np.array_equal(got, want), f"{np.argwhere(got != want)[:4].tolist()}"
+    if aw >= 8 and ah >= 2:                                  # a window that starts at x0 > 0, caller-supplied min/max
+        sub, _, _ = g.render_view(aw - 5, ah - 1, x0=5, minmax=(mn, mx))
+        assert np.array_equal(sub, want[:ah - 1, 5:aw])
+
+
+def test_render_view_goldens_and_saturating_casts():
+    z = np.load(__import__("os").path.join(__import__("tests.helpers", fromlist=["GOLDEN"]).GOLDEN, "render_view.npz"))
+    g = tfs.FluidSim(40, 36)
+    g.write_field(tfs.FIELD_P, z["synthetic_p"]); g.write_field(tfs.FIELD_S, z["synthetic_s"])
+    g.write_field(tfs.FIELD_M, z["synthetic_m"])
+    cells, mn, mx = g.render_view(40, 18)
+    assert np.array_equal(cells, z["synthetic"])             # NaN pressure/smoke, smoke outside [0, 1], every colour arm
+    assert np.array_equal(np.array([mn, mx], np.float32), z["synthetic_minmax"])
+    for name in ("term_80x48_disc", "term_48x42_random_gravity", "odd_37x23"):
+        zz, prm = load_golden(name)
+        st = max(prm["keep"])
+        s = tfs.FluidSim(prm["W"], prm["H"])
+        s.write_field(tfs.FIELD_P, zz[f"p_step{st}"]); s.write_field(tfs.FIELD_S, zz[f"s_step{st}"])
+        s.write_field(tfs.FIELD_M, zz["mask"])
+        aw, ah = (int(v) for v in z[name + "_area"])
+        cells, mn, mx = s.render_view(aw, ah)
+        assert np.array_equal(cells, z[name]), name
+        assert np.array_equal(np.array([mn, mx], np.float32), z[name + "_minmax"])
+
+
+def test_render_view_rejects_what_the_reference_panics_on():
+    g = tfs.FluidSim(8, 8)
+    with pytest.raises(tfs.TfsError):
+        g.render_view(8, 5)
+    with pytest.raises(tfs.TfsError):
+        g.render_view(9, 4)
+    with pytest.raises(tfs.TfsError):
+        g.render_view(4, 4, x0=5)
+    cells, _, _ = g.render_view(0, 0)
+    assert cells.size == 0
+
+
+# ---- packed two-cells-per-thread advection (k_advect32_pair: taken when H % 256 == 0) ------------
+@pytest.mark.parametrize("W,H,amp,frac", [(96, 256, 120.0, 0.02), (40, 512, 2000.0, 0.02), (300, 768, 30.0, 0.1),
+                                          (64, 256, 0.5, 0.0), (5, 256, 50.0, 0.3)])
+def test_pair_advection_kernel_bit_exact(W, H, amp, frac):
+    g, o = make_pair(W, H, gravity=3.0, iterations=6)
+    if frac:
+        g.scene_random(7, frac_to_threshold(frac)); o.scene_random(7, frac)
+    g.fill_random_velocity(5, amp); o.fill_random_velocity(5, amp)       # amp 2000: every clamp of sample_vector binds
+    for st in range(3):
+        g.phase_advect(DT); o.move_velocity(DT)
+        assert_same(g, o, f"advect {st}", fields="uvs")
+        g.next_step(DT); o.step(DT)
+        assert_same(g, o, f"step {st}")
