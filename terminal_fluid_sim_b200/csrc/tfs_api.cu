@@ -97,6 +97,7 @@ struct tfs_sim {
     } peerL, peerR;
     bool attached = false;
     long long step_seq = 0;        // projections run so far (same on every rank)
+    bool inkernel_halo = false;    // the last projection kernel delivered the left rank's halo itself (step_slab)
     int *d_oob = nullptr;          // device flag: an advection sample fell outside the stored columns
 
     tfs::Grid grid() const { return tfs::Grid{(long long)W, (long long)H, xs0, ncols}; }
@@ -380,7 +381,11 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
             ext.cstride = s->lay.cstride;
             ext.xs0 = s->xs0; ext.ncols = s->ncols; ext.c_lo = s->c_lo; ext.b0 = s->b0; ext.b0_next = s->b0_next;
             ext.seq = s->step_seq;
+            s->inkernel_halo = false;
+            ext.halo_cols = (int)kHalo;
+            ext.inkernel_halo = &s->inkernel_halo;
             if (s->peerL.present) {
+                ext.halo_ready_peerL = sync_slot(s->peerL.base, s->peerL.lay, SYNC_PROJDONE_FROM_R);
                 // set 0 = logical (u, v, p), set 1 = logical (u2, v2, p2) -- the same mapping on every rank
                 for (int f = 0; f < 3; ++f) {
                     ext.peerL_buf[0][f] = peer_logical(s, s->peerL, f);
@@ -393,6 +398,8 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
                 ext.peerL_b0 = s->peerL.b0;
             }
             if (s->peerR.present) {
+                ext.wait_right_halo = sync_slot(s->arena, s->lay, SYNC_PUSHB_FROM_R);
+                ext.wait_right_halo_value = s->step_seq - 1;
                 ext.peerR_bnd = reinterpret_cast<float4 *>(s->peerR.base + s->peerR.lay.off_bnd);
                 ext.peerR_cnt = reinterpret_cast<long long *>(s->peerR.base + s->peerR.lay.off_cnt);
                 ext.peerR_cstride = s->peerR.lay.cstride;
@@ -478,13 +485,13 @@ int phase_advect(tfs_sim *s, float dt) {
 // ---- x-slab halo exchange ------------------------------------------------------------------------
 // Copy `ncopy` owned boundary columns of the logical fields in `which` into the neighbours' halo
 // columns (peer stores over NVLink), then raise `flag_idx_*` in the neighbours' sync areas to `seq`.
-int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq) {
+int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq, bool to_left = true) {
     const long long H = (long long)s->H;
     const long long n4 = kHalo * H / 4;
     const unsigned gb = std::min<unsigned>(blocks_for(n4, 256), 148 * 4);
     for (int side = 0; side < 2; ++side) {
         tfs_sim::Peer &p = side == 0 ? s->peerL : s->peerR;
-        if (!p.present) continue;
+        if (!p.present || (side == 0 && !to_left)) continue;
         // to the left rank: my first kHalo owned columns -> its right halo; to the right rank: my last kHalo -> its left halo
         const long long col = side == 0 ? s->c_lo : s->c_hi - kHalo;
         for (int i = 0; i < nwhich; ++i) {
@@ -502,8 +509,8 @@ int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int
 }
 
 int flags_wait(tfs_sim *s, int idx_from_l, int idx_from_r, long long value) {
-    const long long *fl = s->peerL.present ? sync_slot(s->arena, s->lay, idx_from_l) : nullptr;
-    const long long *fr = s->peerR.present ? sync_slot(s->arena, s->lay, idx_from_r) : nullptr;
+    const long long *fl = (s->peerL.present && idx_from_l >= 0) ? sync_slot(s->arena, s->lay, idx_from_l) : nullptr;  // idx < 0: no wait
+    const long long *fr = (s->peerR.present && idx_from_r >= 0) ? sync_slot(s->arena, s->lay, idx_from_r) : nullptr;
     if (!fl && !fr) return TFS_OK;
     tfs::k_flag_wait2<<<1, 1, 0, s->stream>>>(fl, fr, value);
     s->launches++;
@@ -519,17 +526,25 @@ int flags_signal(tfs_sim *s, int idx_for_left_rank, int idx_for_right_rank, long
 }
 
 // One step of an x-slab handle.  Everything is asynchronous on the stream; cross-rank ordering is by
-// sequence flags in device memory (no host synchronisation, so ranks may also share one host thread):
-//   P  wait pushB(seq-1) from the right rank (u halo column of the post-advection field); projection;
-//      raise projdone(seq) at the left rank, wait for the right rank's projdone(seq)
-//   A1 wait advdone(seq-1) from both; push post-projection u, v halos; raise pushA(seq)
-//   A2 wait pushA(seq) from both; advect the owned columns
+// sequence flags in device memory (no host synchronisation, so ranks may also share one host thread).
+// The wave of the exact sweep reaches rank r+1 later than rank r (one band = ~36 us at 32768 rows), so in
+// steady state every rank runs the same schedule shifted by that skew; the hand-offs below are placed so
+// that no rank has to wait for a WHOLE kernel of its right neighbour, which would cost the skew each time:
+//   P  wait pushB(seq-1) from the left rank only.  The projection kernel itself waits for the right rank's
+//      pushB(seq-1) - in its last local band, the only one that reads the right halo (and writes into the
+//      right rank's memory) - and, in its last pass, band 0 stores the left rank's halo columns and last
+//      owned columns and raises haloready(seq) there (the PROJDONE slot) as soon as they are complete.
+//   A1 wait haloready(seq) from the right rank (it also finishes my last KB-1 columns) and advdone(seq-1) from
+//      both; push post-projection u, v to the RIGHT rank; raise pushA(seq) there
+//   A2 wait pushA(seq) from the left rank; advect the owned columns
 //   A3 raise advdone(seq); push post-advection u, v, s halos; raise pushB(seq)
+// Shapes whose band 0 does not cover the halo (KB + kHalo - 1 > 32) fall back to whole-kernel flags:
+// projdone(seq) after the kernel, pushA in both directions.
 int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
     NEED(s->attached, TFS_ERR_COMM, "x-slab handle: call tfs_peer_attach before stepping");
     NEED(s->opt.iterations > 0, TFS_ERR_INVALID_ARG, "x-slab handles need iterations >= 1");
     const long long seq = ++s->step_seq;
-    int rc = flags_wait(s, SYNC_PUSHB_FROM_L, SYNC_PUSHB_FROM_R, seq - 1);
+    int rc = flags_wait(s, SYNC_PUSHB_FROM_L, -1, seq - 1);
     if (rc) return rc;
     if (ev) CU(cudaEventRecord(ev[1], s->stream));
     bool gravity_done = false;
@@ -538,21 +553,28 @@ int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
     if (!gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
     if (ev) CU(cudaEventRecord(ev[2], s->stream));
     const int uv[2] = {0, 1}, uvs[3] = {0, 1, 3};
-    // The right rank's first band writes the final values of my last KB-1 owned columns (and my first
-    // halo column) straight into my memory: my projection result is complete only once ITS kernel is.
-    if (s->peerL.present) {
-        tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(s->peerL.base, s->peerL.lay, SYNC_PROJDONE_FROM_R), seq);
-        s->launches++;
+    const bool fine = s->inkernel_halo;
+    if (!fine) {
+        // The right rank's first band writes the final values of my last KB-1 owned columns (and my first
+        // halo column) straight into my memory: my projection result is complete only once ITS kernel is.
+        if (s->peerL.present) {
+            tfs::k_flag_set<<<1, 1, 0, s->stream>>>(sync_slot(s->peerL.base, s->peerL.lay, SYNC_PROJDONE_FROM_R), seq);
+            s->launches++;
+        }
+        rc = flags_wait(s, -1, SYNC_PROJDONE_FROM_R, seq);
+        if (rc) return rc;
     }
-    if (s->peerR.present) {
-        tfs::k_flag_wait2<<<1, 1, 0, s->stream>>>(nullptr, sync_slot(s->arena, s->lay, SYNC_PROJDONE_FROM_R), seq);
-        s->launches++;
+    else {
+        // haloready(seq): the right rank's band 0 has finished my last KB-1 owned columns (which I am about to
+        // push back to it as its left halo) and my right halo.  It trails my own last band by two bands only.
+        rc = flags_wait(s, -1, SYNC_PROJDONE_FROM_R, seq);
+        if (rc) return rc;
     }
     rc = flags_wait(s, SYNC_ADVDONE_FROM_L, SYNC_ADVDONE_FROM_R, seq - 1);
     if (rc) return rc;
-    rc = halo_push(s, uv, 2, SYNC_PUSHA_FROM_R, SYNC_PUSHA_FROM_L, seq);
+    rc = halo_push(s, uv, 2, SYNC_PUSHA_FROM_R, SYNC_PUSHA_FROM_L, seq, /*to_left=*/!fine);
     if (rc) return rc;
-    rc = flags_wait(s, SYNC_PUSHA_FROM_L, SYNC_PUSHA_FROM_R, seq);
+    rc = flags_wait(s, SYNC_PUSHA_FROM_L, fine ? -1 : SYNC_PUSHA_FROM_R, seq);
     if (rc) return rc;
     rc = phase_advect(s, dt);
     if (rc) return rc;

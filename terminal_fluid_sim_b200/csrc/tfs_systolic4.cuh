@@ -64,6 +64,11 @@ struct Sys4Slab {
     int cnt_strideR = 0;
     long long *out_prog_peerL = nullptr;        // left rank's out_prog mailbox (its index nbL+1), row stride cnt_strideL
     int cnt_strideL = 0;
+    // fine-grained hand-offs with the neighbours' STREAMS (null / 0: the host orders these with whole-kernel flags)
+    const long long *wait_right_halo = nullptr;  // my flag the right rank raises after pushing its post-advection halo:
+    long long wait_right_halo_value = 0;         //   the last local band waits for it before its first load of pass 0
+    long long *halo_ready_peerL = nullptr;       // left rank's flag: raised (to seq) once my band 0 has stored, in the LAST pass,
+    int halo_cols = 0;                           //   its last owned columns and its halo columns [c_lo, c_lo + halo_cols)
 };
 
 struct Sys4Params {
@@ -74,6 +79,9 @@ struct Sys4Params {
     long long *bnd_prog64;  // [n_passes][nb_local + 2]: index 0 = mailbox written by the left rank
     long long *out_prog64;  // [n_passes][nb_local + 2]: index nb_local + 1 = mailbox written by the right rank
     int cstride;            // row stride of the two counter arrays (>= nb_local + 2)
+#ifdef TFS_TASK_TRACE
+    unsigned long long *ttrace;  // [n_tasks][4]: globaltimer at task start / end, SM id, first compute step time
+#endif
 };
 
 TFS_DEVINL long long ld_volatile64(const long long *p) { return *reinterpret_cast<const volatile long long *>(p); }
@@ -129,9 +137,18 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
     const Sys4Slab &SL = P4.slab;
     const int cstride = P4.cstride;
 
+#ifdef TFS_TASK_TRACE
+    int tt_prev = -1;
+#endif
     for (;;) {
         __syncthreads();  // previous task fully retired (smem and mbarrier reuse)
         if (threadIdx.x == 0) {
+#ifdef TFS_TASK_TRACE
+            {
+                unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (tt_prev >= 0) P4.ttrace[4 * tt_prev + 1] = now;
+            }
+#endif
             sm.task = atomicAdd(P.ticket, 1);
             for (int i = 0; i < NS_IN; ++i) { mbar_init(&sm.in_full[i], 32); mbar_init(&sm.in_empty[i], 1); }
             for (int i = 0; i < NR; ++i) { mbar_init(&sm.rec_full[i], 32); mbar_init(&sm.rec_empty[i], NW); }
@@ -142,6 +159,14 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
         __syncthreads();
         const int ticket = sm.task;
         if (ticket >= n_tasks) break;
+#ifdef TFS_TASK_TRACE
+        if (threadIdx.x == 0) {
+            unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P4.ttrace[4 * ticket] = now; P4.ttrace[4 * ticket + 2] = smid;
+            tt_prev = ticket;
+        }
+#endif
         const int2 tk = P4.tasks[ticket];
         const int tb = tk.x, b = tk.y, lb = tk.y - SL.b0;  // pass, global band, local band
         const int par = tb & 1;
@@ -174,6 +199,14 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
             const unsigned char *bf = P.flags - SL.xs0 * H;
             const long long cs0 = SL.xs0, cs1 = SL.xs0 + SL.ncols;  // stored columns
 
+            if (first_pass && last_local && SL.wait_right_halo) {
+                // column c_hi (u of the right rank's first column, after ITS advection of the previous step) is read below;
+                // the same flag says the right rank's previous kernel is over, so its record slot 0 and mailboxes are free
+                if (lane == 0)
+                    while (ld_volatile64(SL.wait_right_halo) < SL.wait_right_halo_value) __nanosleep(1000);
+                __syncwarp();
+                fence_sys();
+            }
             auto load_block = [&](int n) {
                 // rows [RB*n, RB*n + RB) of columns q0.. (u: q0+1..) -> slot n % NS_IN
                 const int slot = n % NS_IN;
@@ -277,6 +310,9 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                 pp_ = SL.peerL_buf[(tb + 1) & 1][2] - SL.peerL_xs0 * H;
             }
             const long long c_lo = SL.c_lo;
+            // last pass: band 0 also delivers the left rank's right-halo columns (u, v of [c_lo, c_lo + halo_cols))
+            const bool halo_pass = pu && SL.halo_ready_peerL && tb == P.n_passes - 1;
+            const long long c_peer_hi = halo_pass ? c_lo + SL.halo_cols - 1 : c_lo;  // last column copied to the left rank
             int m_next = 0, rows_done = 0;
             // block m (rows [32m, 32m+32)) is complete once lane 31 retired its last row
             auto done_step = [&](int m) { return min(RB * m + (RB - 1) + 31 + KB, T - 1); };
@@ -300,10 +336,10 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                                 *reinterpret_cast<float4 *>(lv + idx) = vv;
                                 *reinterpret_cast<float4 *>(lp + idx) = vp;
                             }
-                            if (pu && col <= c_lo) {  // owned by (or the first halo column of) the left rank
+                            if (pu && col <= c_peer_hi) {  // owned by (or a halo column of) the left rank
                                 *reinterpret_cast<float4 *>(pu + idx) = vu;
                                 *reinterpret_cast<float4 *>(pv + idx) = vv;
-                                *reinterpret_cast<float4 *>(pp_ + idx) = vp;
+                                if (col <= c_lo) *reinterpret_cast<float4 *>(pp_ + idx) = vp;
                             }
                         }
                     }
@@ -334,6 +370,8 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                     }
                     for (int m = m_first; m < m_next; ++m) mbar_arrive(&sm.out_empty[m % NS_OUT]);
                     mbar_arrive(&sm.pub_done[j % NPH]);
+                    // everything this band owes the left rank for this step is stored and fenced (system scope: lb == 0)
+                    if (halo_pass && j == n_int - 1) st_volatile64(SL.halo_ready_peerL, seq);
                 }
             }
 #ifdef TFS_SYS_TRACE
@@ -591,6 +629,11 @@ struct Sys4External {
     // right neighbour
     float4 *peerR_bnd = nullptr;
     long long *peerR_cnt = nullptr; int peerR_cstride = 0, peerR_b0 = 0, peerR_b0_next = -1;
+    // in-kernel hand-offs (see Sys4Slab); halo_cols > 0 asks for them, *inkernel_halo reports whether the chosen
+    // shape can deliver the halo from band 0 alone (KB + halo_cols - 1 <= 32)
+    const long long *wait_right_halo = nullptr; long long wait_right_halo_value = 0;
+    long long *halo_ready_peerL = nullptr; int halo_cols = 0;
+    bool *inkernel_halo = nullptr;
 };
 
 struct Systolic4Workspace {
@@ -673,6 +716,16 @@ struct Sys4Launch {
                 SL.out_prog_peerL = ext->peerL_cnt + (size_t)ext->peerL_max_passes * ext->peerL_cstride + (nbL + 1);
                 SL.cnt_strideL = ext->peerL_cstride;
             }
+            SL.wait_right_halo = ext->wait_right_halo;
+            SL.wait_right_halo_value = ext->wait_right_halo_value;
+            // band b0 stores the columns [c_lo - KB + 1, c_lo + 33 - KB): with this shape, do they include the halo?
+            // (a property of the shape alone, so every rank reaches the same answer)
+            const bool halo_fits = ext->halo_cols > 0 && KB + ext->halo_cols - 1 <= 32;
+            if (ext->inkernel_halo) *ext->inkernel_halo = halo_fits;
+            if (halo_fits && ext->halo_ready_peerL) {
+                SL.halo_ready_peerL = ext->halo_ready_peerL;
+                SL.halo_cols = ext->halo_cols;
+            }
             if (ext->peerR_bnd) {
                 const int nbR = (ext->peerR_b0_next >= 0 ? ext->peerR_b0_next : P.n_bands) - ext->peerR_b0;
                 SL.rec_peerR[0] = ext->peerR_bnd;
@@ -747,9 +800,37 @@ struct Sys4Launch {
         cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), a.stream);
         P.trace = d_trace;
 #endif
+#ifdef TFS_TASK_TRACE
+        // debug build only: per-task start / end times, dumped to $TFS_TASK_TRACE_PREFIX.b<first band>.bin after every launch
+        static unsigned long long *d_tt[64] = {nullptr};
+        static size_t d_tt_cap[64] = {0};
+        if (d_tt_cap[di] < (size_t)n_tasks) {
+            if (d_tt[di]) cudaFree(d_tt[di]);
+            cudaMalloc((void **)&d_tt[di], (size_t)n_tasks * 4 * sizeof(unsigned long long));
+            d_tt_cap[di] = (size_t)n_tasks;
+        }
+        cudaMemsetAsync(d_tt[di], 0, (size_t)n_tasks * 4 * sizeof(unsigned long long), a.stream);
+        P4.ttrace = d_tt[di];
+#endif
         kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
+#ifdef TFS_TASK_TRACE
+        if (const char *pre = getenv("TFS_TASK_TRACE_PREFIX")) {
+            cudaStreamSynchronize(a.stream);
+            std::vector<unsigned long long> h((size_t)n_tasks * 4);
+            cudaMemcpy(h.data(), d_tt[di], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            char path[512];
+            snprintf(path, sizeof(path), "%s.b%d.bin", pre, SL.b0);
+            if (FILE *f = fopen(path, "wb")) {
+                const long long hdr[8] = {n_tasks, P.n_passes, SL.nb_local, SL.b0, grid, P.T, KB, 0};
+                fwrite(hdr, sizeof(hdr), 1, f);
+                fwrite(ws4.h_tasks, sizeof(int2), (size_t)n_tasks, f);
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                fclose(f);
+            }
+        }
+#endif
 #ifdef TFS_SYS_TRACE
         {
             long long h[64 * 8];
