@@ -793,7 +793,13 @@ struct Sys4Launch {
         }
         const int occ = occ_dev[di];
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
-        const int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
+        int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
+        if (const char *ge = getenv("TFS_SYS_GRID")) {  // tuning aid: "even" = whole rounds, or a CTA count
+            if (ge[0] == 'e') {
+                const long long rounds = (n_tasks + grid - 1) / grid;
+                grid = (int)((n_tasks + rounds - 1) / rounds);
+            } else if (atoi(ge) > 0) grid = std::min(grid, atoi(ge));
+        }
 #ifdef TFS_SYS_TRACE
         static long long *d_trace = nullptr;
         if (!d_trace) cudaMalloc((void **)&d_trace, 64 * 8 * sizeof(long long));
