@@ -170,16 +170,23 @@ def run_ours(args):
     adv_ms = phases["advect_ms"] / max(1, phases["steps"])
     alg_bytes = 25.0 * K * cells                                  # 25 B / cell / iteration
     achieved = alg_bytes / (proj_ms / 1e3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of the projection kernel, per launch, from the ncu captures
+    # committed under profiles/ (a separate run of the same configuration; never measured inside this timed run)
+    traffic = {"c5": (4.658e11, "profiles/r01_c5_dram_32768_K200.csv"),
+               "c3": (2.30e9, "profiles/r01_systolic4_c3_4096_K100.txt")}.get(args.workload, (None, None))
     roofline = {"kernel": "k_project_systolic4 (gravity + %d-iteration exact projection)" % K, "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": round(proj_ms, 4),
+                "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src, "ms_per_launch": round(proj_ms, 4),
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "advect": {"ms_per_launch": round(adv_ms, 4), "achieved": round(25.0 * cells / (adv_ms / 1e3) / 1e9, 1),
                            "frac": round(25.0 * cells / (adv_ms / 1e3) / 1e9 / peak, 4)}}
 
     # ---- e2e: public API with host buffers -----------------------------------------------------------
+    # the frame consumer is the renderer (src/ui/sim_renderer.rs): a terminal area of aw x ah cells shows the
+    # aw x 2*ah sim cells at the top left; tfs_render_view returns their colours (min/max scan included)
     vx, vy, vw, vh = view_window(W, H)
-    pin_s, pin_p = tfs.PinnedBuffer(vw * vh), tfs.PinnedBuffer(vw * vh)
+    aw, ah = vw, vh // 2
+    pin_c = tfs.PinnedBuffer(max(1, aw * ah * 8), np.uint8)
     pin_m = tfs.PinnedBuffer(H, np.uint8)
     pin_m.array[:] = 0
     e2e_steps = max(1, args.steps)
@@ -190,9 +197,7 @@ def run_ours(args):
         pin_m.array[H // 2 - 4:H // 2 + 4] = 1
         sim.upload_blocks(pin_m.array, offset=x * H)               # H2D (dirty range) -> flags refresh
         sim.next_step(DT)
-        sim.read_view(tfs.FIELD_S, vx, vy, vw, vh, out=pin_s.array)   # D2H
-        sim.read_view(tfs.FIELD_P, vx, vy, vw, vh, out=pin_p.array)   # D2H
-        return sim.pressure_minmax()                               # D2H (2 floats)
+        return sim.render_view(aw, ah, out=pin_c.array[:aw * ah * 8])   # device colour loop, D2H 8 B per terminal cell
 
     e2e_step(0)
     sim.sync()
@@ -202,10 +207,10 @@ def run_ours(args):
     sim.sync()
     e2e_s = time.perf_counter() - t0
     e2e = {"value": round(cells * e2e_steps / e2e_s / 1e9, 4), "unit": "Gcell-steps/s",
-           "h2d_bytes_per_step": int(H), "d2h_bytes_per_step": int(2 * vw * vh * 4 + 8),
-           "what": "upload_blocks(1 column) + next_step + read_view(smoke, pressure %dx%d window) + pressure_minmax; "
-                   "host wall clock" % (vw, vh)}
-    pin_s.close(); pin_p.close(); pin_m.close()
+           "h2d_bytes_per_step": int(H), "d2h_bytes_per_step": int(aw * ah * 8 + 8),
+           "what": "upload_blocks(1 column) + next_step + render_view(%dx%d terminal cells = %dx%d sim window: pressure "
+                   "min/max, gradient, smoke, blocks on the device); host wall clock" % (aw, ah, vw, vh)}
+    pin_c.close(); pin_m.close()
     launches_per_step = (l_after - l_before) / max(1, args.steps)
     sim.close()
 
@@ -223,7 +228,7 @@ def run_ours(args):
         pj, ad = ph3["project_ms"] / ph3["steps"], ph3["advect_ms"] / ph3["steps"]
         extra["config3_4096"] = {
             "workload": w3["name"], "value": round(c3 * 10 / (ms3 / 1e3) / 1e9, 4), "unit": "Gcell-steps/s",
-            "ncu_dram_bytes_per_projection_launch": 1.90e9, "ncu_source": "profiles/r01_systolic4_c3_4096_K100.txt",
+            "ncu_dram_bytes_per_projection_launch": 2.30e9, "ncu_source": "profiles/r01_systolic4_c3_4096_K100.txt",
             "ms_per_step": round(ms3 / 10, 4),
             "project": {"ms": round(pj, 4), "achieved_gbs": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9, 1),
                         "frac": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9 / peak, 4)},
