@@ -259,3 +259,17 @@ def test_pair_advection_kernel_bit_exact(W, H, amp, frac):
         assert_same(g, o, f"advect {st}", fields="uvs")
         g.next_step(DT); o.step(DT)
         assert_same(g, o, f"step {st}")
+
+
+@pytest.mark.parametrize("kernel", EXACT_KERNELS)
+def test_3x3_projection_known_answer_from_source_text(kernel):
+    """The hand-worked value of tests/test_oracle.py::test_3x3_projection_worked_by_hand_from_the_source_text,
+    on the device: correction = 1.9 * (50 / 3) at the only updatable cell of a 3x3 grid."""
+    f = np.float32
+    c = f(1.9) * (f(50.0) / f(3.0))
+    pc = f(1000.0) / f(DT)
+    g = tfs.FluidSim(3, 3, iterations=1, kernel=kernel)
+    g.phase_project(DT)
+    u, v, p = g.u, g.v, g.p
+    assert u[4] == f(50.0) and u[7] == c and v[4] == -c and v[5] == c and p[4] == pc * c
+    assert np.count_nonzero(v) == 2 and np.count_nonzero(p) == 1 and np.count_nonzero(u) == 4

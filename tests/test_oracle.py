@@ -83,6 +83,30 @@ def test_default_2x2_is_noop():
     assert bits_equal(o.u, u0) and bits_equal(o.s, s0)
 
 
+def test_3x3_projection_worked_by_hand_from_the_source_text():
+    """Known-answer value derived from simulator.rs by hand, independent of both restatements.
+
+    3x3 grid, default config (wind 50, density 1000), one iteration, dt = 1/60, no gravity: the only cell that is
+    neither block nor border is (1, 1), idx 4 (simulator.rs:161, :365-375).  Column 0 is solid (:113-119) and
+    set_horizontal_speed wrote u[3..6) = 50 (:79-85).  Around idx 4: top 5, right 7, bottom 3, left 1 (:343-350);
+    only the LEFT neighbour is a block, so sT = sR = sB = 1, sL = 0 and n = 3 (:165-170).
+    divergence = ((u[7] - u[4]) + v[5]) - v[4] = (0 - 50) + 0 - 0 = -50 (:176-178);
+    correction = 1.9 * (50 / 3) (:180); u[4] -= c*0, u[7] += c, v[4] -= c, v[5] += c (:181-185);
+    p[4] += (1000 / dt) * c (:155, :186)."""
+    f = np.float32
+    c = f(1.9) * (f(50.0) / f(3.0))
+    pc = f(1000.0) / f(DT)
+    o = OracleSim(3, 3, iterations=1)
+    o.make_incompressible(DT)
+    u, v, p = o.u, o.v, o.p
+    assert u[4] == f(50.0) and u[7] == c and v[4] == -c and v[5] == c and p[4] == pc * c
+    assert u[3] == 50.0 and u[5] == 50.0                    # the border cells of column 1 keep their wind
+    assert np.count_nonzero(v) == 2 and np.count_nonzero(p) == 1 and np.count_nonzero(u) == 4
+    n = NpSim(3, 3, iterations=1)
+    n.make_incompressible(DT)
+    assert bits_equal(n.u, u) and bits_equal(n.v, v) and bits_equal(n.p, p)
+
+
 def test_initial_state_matches_reference_constants():
     o = OracleSim(100, 100)
     H = 100
