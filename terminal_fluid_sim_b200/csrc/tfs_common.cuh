@@ -18,6 +18,22 @@
 #define TFS_F_T 8u   // top neighbour is fluid    (:165)
 #define TFS_F_LIVE 16u  // !block && !border      (:161)
 
+// Every wait on another GPU (or on another CTA through global memory) is bounded: if the awaited value has not
+// arrived after TFS_SPIN_TIMEOUT_NS the kernel traps, so a rank that died or a protocol error surfaces as a
+// CUDA error on every rank instead of hanging the box.  Only the slow path (already sleeping) reads the timer.
+#ifndef TFS_SPIN_TIMEOUT_NS
+#define TFS_SPIN_TIMEOUT_NS 30000000000ULL
+#endif
+TFS_DEVINL unsigned long long tfs_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct SpinGuard {
+    unsigned long long t0 = 0;
+    TFS_DEVINL void tick() {  // call once per unsuccessful poll
+        const unsigned long long now = tfs_now_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > TFS_SPIN_TIMEOUT_NS) __trap();
+    }
+};
+
 TFS_DEVINL float fadd(float a, float b) { return __fadd_rn(a, b); }
 TFS_DEVINL float fsub(float a, float b) { return __fsub_rn(a, b); }
 TFS_DEVINL float fmul(float a, float b) { return __fmul_rn(a, b); }

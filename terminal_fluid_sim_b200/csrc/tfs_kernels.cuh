@@ -571,8 +571,9 @@ __global__ void k_flag_set(long long *flag, long long value) {
 }
 __global__ void k_flag_wait2(const long long *f0, const long long *f1, long long value) {
     // f0 / f1 may be null (no neighbour on that side)
-    if (f0) while (*reinterpret_cast<const volatile long long *>(f0) < value) {}
-    if (f1) while (*reinterpret_cast<const volatile long long *>(f1) < value) {}
+    SpinGuard guard;
+    if (f0) while (*reinterpret_cast<const volatile long long *>(f0) < value) { __nanosleep(200); guard.tick(); }
+    if (f1) while (*reinterpret_cast<const volatile long long *>(f1) < value) { __nanosleep(200); guard.tick(); }
     __threadfence_system();
 }
 

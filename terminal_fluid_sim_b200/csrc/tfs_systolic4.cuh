@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4
                 // column c_hi (u of the right rank's first column, after ITS advection of the previous step) is read below;
                 // the same flag says the right rank's previous kernel is over, so its record slot 0 and mailboxes are free
                 if (lane == 0)
-                    while (ld_volatile64(SL.wait_right_halo) < SL.wait_right_halo_value) __nanosleep(1000);
+                    for (SpinGuard guard; ld_volatile64(SL.wait_right_halo) < SL.wait_right_halo_value; guard.tick()) __nanosleep(1000);
                 __syncwarp();
                 fence_sys();
             }
