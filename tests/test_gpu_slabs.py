@@ -61,6 +61,26 @@ def test_slabs_match_oracle_bit_exact(world, W, H, K, tb, g):
     grp.close()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_config4_like_lattice_slabs_equal_single_gpu_bitwise(world):
+    """SURVEY 8d config 4, scaled down: wind tunnel with a lattice of discs, K = 50; the x-slab run must equal the
+    single-GPU run bit for bit (the single-GPU kernel is itself pinned to the oracle by the other tests)."""
+    if _ndev() < world:
+        pytest.skip(f"needs {world} GPUs")
+    W, H, K = 4096, 1024, 50
+    one = tfs.FluidSim(W, H, iterations=K)
+    grp = tfs.SlabGroup(W, H, world=world, iterations=K)
+    one.scene_lattice(512, 48); grp.each("scene_lattice", 512, 48)
+    for _ in range(3):
+        one.next_step(DT); grp.next_step(DT)
+    one.sync(); grp.sync()
+    for f, n in FIELDS:
+        a, b = grp.read_field(f), one.read_field(f)
+        assert bits_equal(a, b), f"world={world} {n}: " + first_mismatch(a, b, H)
+    assert np.array_equal(grp.read_field(tfs.FIELD_M), one.read_field(tfs.FIELD_M))
+    one.close(); grp.close()
+
+
 def test_slab_handle_rejects_what_it_cannot_do():
     if _ndev() < 2:
         pytest.skip("needs 2 GPUs")
