@@ -38,7 +38,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DT = float(np.float32(1.0 / 60.0))
+MODES = {"exact": 0, "rb": 1}
+MODE_NAME = {"exact": "wavefront_exact", "rb": "red_black (temporally blocked, tolerance-checked)"}
 WORKLOADS = {
+    "c1": dict(name="config1: the reference's cargo bench, 100x100, default config, K=50, dt=1/60", W=100, H=100, K=50,
+               gravity=0.0, scene="none"),
+    "c4": dict(name="config4: 16384^2 wind tunnel, discs r=96 on a 1024-pitch lattice, K=50, dt=1/60", W=16384, H=16384, K=50,
+               gravity=0.0, scene="lattice"),
     "c5": dict(name="config5: 32768^2 random obstacles 2% (seed 0x5EED), K=200, dt=1/60", W=32768, H=32768, K=200,
                gravity=0.0, scene="random"),
     "c3": dict(name="config3: 4096^2 smoke plume, gravity 9.8, K=100, dt=1/60", W=4096, H=4096, K=100, gravity=9.8,
@@ -110,6 +116,12 @@ def setup_scene(sim, wl):
         sim.scene_random(0x5EED, (2 << 64) // 100)
     elif wl["scene"] == "disc":
         sim.scene_disc(256, 512, 128)
+    elif wl["scene"] == "lattice":
+        sim.scene_lattice(1024, 96)
+
+
+def hexsum(cs):
+    return ["%016x" % int(x) for x in cs]
 
 
 def view_window(W, H):
@@ -147,9 +159,8 @@ def run_ours(args):
     if world > 1:
         return run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src)
 
-    sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank)
+    sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank, mode=MODES[args.mode])
     setup_scene(sim, wl)
-    launches0 = sim.launch_count()
     for _ in range(args.warmup):
         sim.next_step(DT)
     sim.sync()
@@ -174,7 +185,11 @@ def run_ours(args):
     # committed under profiles/ (a separate run of the same configuration; never measured inside this timed run)
     traffic = {"c5": (4.658e11, "profiles/r01_c5_dram_32768_K200.csv"),
                "c3": (2.30e9, "profiles/r01_systolic4_c3_4096_K100.txt")}.get(args.workload, (None, None))
-    roofline = {"kernel": "k_project_systolic4 (gravity + %d-iteration exact projection)" % K, "bound": "hbm",
+    kname = "k_project_systolic4 (gravity + %d-iteration exact projection)" if args.mode == "exact" else \
+        "k_project_rb (gravity + %d red-black iterations, 4 per launch; all launches of a step)"
+    if args.mode != "exact":
+        traffic = (None, None)
+    roofline = {"kernel": kname % K, "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src, "ms_per_launch": round(proj_ms, 4),
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -212,37 +227,19 @@ def run_ours(args):
                    "min/max, gradient, smoke, blocks on the device); host wall clock" % (aw, ah, vw, vh)}
     pin_c.close(); pin_m.close()
     launches_per_step = (l_after - l_before) / max(1, args.steps)
+    # parity evidence: order-independent checksum of the bit patterns of u, v, p, s after the whole deterministic
+    # sequence (warm-up, timed steps, e2e steps with their brush edits).  The same command at N = 2, 4, 8 must print
+    # the same eight words: the x-slab run then equals the single-GPU run bit for bit.
+    parity = {"checksum": hexsum(sim.checksum()), "steps": args.warmup + args.steps + 1 + e2e_steps,
+              "what": "sum / xor of 64-bit hashes of (cell index, f32 bits) of u, v, p, s over the whole grid (tfs_checksum)"}
+    proj_info = sim.last_projection()
     sim.close()
 
-    # ---- extra: config 3 in the same run (the >= 60 %-of-roofline target of the north star) ----------
+    # ---- extra: config 3 (the >= 60 %-of-roofline target of the north star) and config 4, both modes ----
     extra = {}
     if args.workload == "c5" and not args.no_extra:
-        w3 = WORKLOADS["c3"]
-        s3 = tfs.FluidSim(w3["W"], w3["H"], tfs.SimConfig(gravity=w3["gravity"]), iterations=w3["K"], device=local_rank)
-        for _ in range(3):
-            s3.next_step(DT)
-        s3.set_profiling(True)
-        ms3 = time_steps(s3, 10)
-        ph3 = s3.phase_ms()
-        c3 = w3["W"] * w3["H"]
-        pj, ad = ph3["project_ms"] / ph3["steps"], ph3["advect_ms"] / ph3["steps"]
-        extra["config3_4096"] = {
-            "workload": w3["name"], "value": round(c3 * 10 / (ms3 / 1e3) / 1e9, 4), "unit": "Gcell-steps/s",
-            "ncu_dram_bytes_per_projection_launch": 2.30e9, "ncu_source": "profiles/r01_systolic4_c3_4096_K100.txt",
-            "ms_per_step": round(ms3 / 10, 4),
-            "project": {"ms": round(pj, 4), "achieved_gbs": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9, 1),
-                        "frac": round(25.0 * w3["K"] * c3 / (pj / 1e3) / 1e9 / peak, 4)},
-            "advect": {"ms": round(ad, 4), "achieved_gbs": round(25.0 * c3 / (ad / 1e3) / 1e9, 1),
-                       "frac": round(25.0 * c3 / (ad / 1e3) / 1e9 / peak, 4)}}
-        # red-black mode on the same grid
-        s3.close()
-        s3 = tfs.FluidSim(w3["W"], w3["H"], tfs.SimConfig(gravity=w3["gravity"]), iterations=w3["K"],
-                          mode=tfs.MODE_RED_BLACK, device=local_rank)
-        for _ in range(2):
-            s3.next_step(DT)
-        ms3rb = time_steps(s3, 5)
-        extra["config3_4096"]["red_black_ms_per_step"] = round(ms3rb / 5, 4)
-        s3.close()
+        extra["config3_4096"] = side_workload(tfs, "c3", local_rank, peak, steps=10, warmup=3)
+        extra["config4_16384"] = side_workload(tfs, "c4", local_rank, peak, steps=5, warmup=3)
 
     cpu = cpu_baseline(args.workload, steps=2, warmup=1) if not args.no_cpu else None
 
@@ -250,14 +247,72 @@ def run_ours(args):
         "metric": "Gcell-steps/s", "value": round(value, 4), "unit": "Gcell-steps/s", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "grid": [W, H], "pressure_iterations": K, "mode": "wavefront_exact",
+        "config": {"workload": wl["name"], "grid": [W, H], "pressure_iterations": K, "mode": MODE_NAME[args.mode],
                    "omega": 1.9, "parallelism": "x-slabs x%d" % n_gpus,
                    "l2": "state (%.1f GB) exceeds L2, no flush needed" % (17 * cells / 1e9)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
-        "gpu_launches_per_step": launches_per_step, "clocks": clocks, "extra": extra,
+        "gpu_launches_per_step": launches_per_step, "clocks": clocks, "parity": parity,
+        "projection_kernel": proj_info, "extra": extra,
     }
     if rank == 0:
         print(json.dumps(out))
+
+
+def side_workload(tfs, key, device, peak, steps, warmup, group=None):
+    """one of the other BASELINE configs measured in the same run, in both projection modes; `group` = (dist, rank,
+    world) runs it on x-slabs.  Returns ms/step, Gcell-steps/s, per-phase roofline fractions and the checksum."""
+    import numpy as _np
+    w = WORKLOADS[key]
+    cells = w["W"] * w["H"]
+    out = {"workload": w["name"]}
+    for mode in ("exact", "rb"):
+        if group is None:
+            s = tfs.FluidSim(w["W"], w["H"], tfs.SimConfig(gravity=w["gravity"]), iterations=w["K"], mode=MODES[mode], device=device)
+        else:
+            dist, rank, world = group
+            s = tfs.FluidSim(w["W"], w["H"], tfs.SimConfig(gravity=w["gravity"]), iterations=w["K"], mode=MODES[mode], device=device,
+                             rank=rank, world=world)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, s.peer_export())
+            s.peer_attach(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+        setup_scene(s, w)
+        s.sync()
+        if group is not None:
+            group[0].barrier()
+        for _ in range(warmup):
+            s.next_step(DT)
+        s.sync()
+        if group is not None:
+            group[0].barrier()
+        s.set_profiling(True)
+        ms = time_steps(s, steps)
+        ph = s.phase_ms()
+        s.set_profiling(False)
+        cs = s.checksum()
+        pj, ad = ph["project_ms"] / max(1, ph["steps"]), ph["advect_ms"] / max(1, ph["steps"])
+        if group is not None:
+            import torch
+            dist, rank, world = group
+            t = torch.tensor([ms, pj, ad], dtype=torch.float64, device=f"cuda:{device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, pj, ad = (float(x) for x in t.tolist())
+            parts = [None] * world
+            dist.all_gather_object(parts, [int(x) for x in cs])
+            cs = tfs.combine_checksums([_np.array(p, dtype=_np.uint64) for p in parts])
+            dist.barrier()
+        n = 1 if group is None else group[2]
+        r = {"ms_per_step": round(ms / steps, 4), "value": round(cells * steps / (ms / 1e3) / 1e9, 4), "unit": "Gcell-steps/s",
+             "project": {"ms": round(pj, 4), "achieved_gbs_per_gpu": round(25.0 * w["K"] * cells / (pj / 1e3) / 1e9 / n, 1),
+                         "frac": round(25.0 * w["K"] * cells / (pj / 1e3) / 1e9 / n / peak, 4)},
+             "advect": {"ms": round(ad, 4), "achieved_gbs_per_gpu": round(25.0 * cells / (ad / 1e3) / 1e9 / n, 1),
+                        "frac": round(25.0 * cells / (ad / 1e3) / 1e9 / n / peak, 4)},
+             "kernel": s.last_projection(), "checksum_after_%d_steps" % (warmup + steps): hexsum(cs)}
+        out[mode] = r
+        s.sync()
+        if group is not None:
+            group[0].barrier()
+        s.close()
+    return out
 
 
 def run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src):
@@ -266,7 +321,8 @@ def run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src)
     hand the IPC blobs around, for the barrier and for the max-over-ranks of the device time."""
     import torch
     W, H, K = wl["W"], wl["H"], wl["K"]
-    sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank, rank=rank, world=world)
+    sim = tfs.FluidSim(W, H, tfs.SimConfig(gravity=wl["gravity"]), iterations=K, device=local_rank, rank=rank, world=world,
+                       mode=MODES[args.mode])
     blobs = [None] * world
     dist.all_gather_object(blobs, sim.peer_export())
     sim.peer_attach(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
@@ -340,18 +396,28 @@ def run_ours_slabs(args, tfs, dist, rank, world, local_rank, wl, peak, peak_src)
     launches_per_step = (l_after - l_before) / max(1, args.steps)
     pin_s.close(); pin_p.close(); pin_m.close()
     sim.sync()
+    parts = [None] * world
+    dist.all_gather_object(parts, [int(x) for x in sim.checksum()])
+    parity = {"checksum": hexsum(tfs.combine_checksums([np.array(p, dtype=np.uint64) for p in parts])),
+              "steps": args.warmup + args.steps + 1 + max(1, args.steps),
+              "what": "sum / xor of 64-bit hashes of (cell index, f32 bits) of u, v, p, s over the whole grid: the per-slab "
+                      "checksums (tfs_checksum) added / xored; equal to the N=1 line's when the x-slab run is bit-identical"}
+    proj_info = sim.last_projection()
     dist.barrier()
     sim.close()
+    extra = {}
+    if args.workload == "c5" and not args.no_extra:
+        extra["config4_16384"] = side_workload(tfs, "c4", local_rank, peak, steps=5, warmup=3, group=(dist, rank, world))
     out = {
         "metric": "Gcell-steps/s", "value": round(value, 4), "unit": "Gcell-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "grid": [W, H], "pressure_iterations": K, "mode": "wavefront_exact",
+        "config": {"workload": wl["name"], "grid": [W, H], "pressure_iterations": K, "mode": MODE_NAME[args.mode],
                    "omega": 1.9, "parallelism": "x-slabs x%d (peer stores over NVLink, no collective)" % world,
                    "l2": "state (%.1f GB) exceeds L2, no flush needed" % (17 * cells / 1e9)},
         "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
         "gpu_launches": int(round(launches_per_step * args.steps)) * world, "gpu_launches_per_step_per_rank": launches_per_step,
-        "clocks": clocks, "extra": {},
+        "clocks": clocks, "parity": parity, "projection_kernel": proj_info, "extra": extra,
     }
     if rank == 0:
         print(json.dumps(out))
@@ -367,6 +433,11 @@ def cpu_sample(workload):
     if workload == "c3":
         return dict(W=1024, H=1024, K=wl["K"], gravity=wl["gravity"], scene="none",
                     desc="1024x1024 sub-grid of config3, K=100")
+    if workload == "c4":
+        return dict(W=2048, H=2048, K=wl["K"], gravity=wl["gravity"], scene="lattice",
+                    desc="2048x2048 sub-grid of config4 (same lattice), K=50")
+    if workload == "c1":
+        return dict(W=100, H=100, K=wl["K"], gravity=0.0, scene="none", desc="full config1 (100x100, K=50)")
     return dict(W=wl["W"], H=wl["H"], K=wl["K"], gravity=wl["gravity"], scene="disc", desc="full config2")
 
 
@@ -378,6 +449,8 @@ def run_cpu(workload, steps, warmup):
         o.L.orc_scene_random(o.h, 0x5EED, frac_to_threshold(0.02))
     elif sm["scene"] == "disc":
         o.scene_disc(256, 512, 128)
+    elif sm["scene"] == "lattice":
+        o.scene_lattice(1024, 96)
     for _ in range(warmup):
         o.step(DT)
     t0 = time.perf_counter()
@@ -417,19 +490,43 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_sweep(args):
+    """--workload all: the deterministic bench harness.  Every BASELINE config on one GPU, both
+    projection modes, next to the CPU restatement of the reference - on the SAME grid for configs 1 and 2, on a
+    stated sub-grid for the larger ones.  One JSON line; BASELINE.md's results table is filled from it."""
+    import terminal_fluid_sim_b200 as tfs
+    peak, peak_src = measured_peaks()
+    rows = []
+    plan = {"c1": (200, 20, 200, 20), "c2": (20, 5, 3, 1), "c3": (10, 3, 2, 1), "c4": (5, 3, 2, 1), "c5": (3, 3, 2, 1)}
+    for key in ("c1", "c2", "c3", "c4", "c5"):
+        gs, gw, cs_, cw = plan[key]
+        row = side_workload(tfs, key, 0, peak, steps=gs, warmup=gw)
+        row["key"] = key
+        if not args.no_cpu:
+            value, ms, sm = run_cpu(key, cs_, cw)
+            row["cpu"] = {"value": round(value, 6), "unit": "Gcell-steps/s", "ms_per_step": round(ms, 3), "cores": os.cpu_count(),
+                          "kind": "port", "sample": sm["desc"], "same_grid": sm["W"] == WORKLOADS[key]["W"]}
+        rows.append(row)
+    print(json.dumps({"sweep": rows, "n_gpus": 1, "dtype": "f32", "data": "synthetic", "peak_hbm_gbs": peak, "peak_source": peak_src,
+                      "unit": "Gcell-steps/s", "dt": DT}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS) + ["all"])
+    ap.add_argument("--mode", default="exact", choices=sorted(MODES), help="projection order of the headline run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 extra measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "all":
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -116,6 +116,8 @@ int tfs_phase_gravity(tfs_sim *sim, float dt);  /* add_gravity         (simulato
 int tfs_phase_project(tfs_sim *sim, float dt);  /* make_incompressible (simulator.rs:151-190) */
 int tfs_phase_advect(tfs_sim *sim, float dt);   /* move_velocity       (simulator.rs:192-243) */
 int tfs_sync(tfs_sim *sim);
+/* non-blocking: *idle = 1 when everything enqueued on the handle's stream has finished */
+int tfs_stream_idle(tfs_sim *sim, int *idle);
 
 /* Copy the window [x0, x0+w) x [y0, y0+h) of a field to host memory, packed column-major
  * (dst[(x-x0)*h + (y-y0)]); synchronises.  This is the per-frame D2H of the visible view
@@ -162,6 +164,28 @@ int tfs_set_profiling(tfs_sim *sim, int enabled);
 int tfs_get_phase_ms(tfs_sim *sim, float *gravity_ms, float *project_ms, float *advect_ms, uint64_t *steps);
 /* kernels launched by this handle since creation */
 int tfs_launch_count(const tfs_sim *sim, uint64_t *launches);
+/* which projection kernel the last tfs_step / tfs_phase_project ran, and its shape */
+typedef enum tfs_projection_kernel {
+    TFS_PROJ_NONE = 0,
+    TFS_PROJ_SYSTOLIC_BLOCK_RING = 1, /* k_project_systolic4: the shipped exact kernel (height % 4 == 0) */
+    TFS_PROJ_SYSTOLIC_GENERIC = 2,    /* k_project_systolic: exact, any height */
+    TFS_PROJ_DIAGONAL = 3,            /* k_project_wavefront: one launch per anti-diagonal */
+    TFS_PROJ_REDBLACK_FUSED = 4,      /* k_project_rb: temporally blocked red-black (even height) */
+    TFS_PROJ_REDBLACK_TWO_LAUNCH = 5  /* k_project_redblack: one launch per colour */
+} tfs_projection_kernel;
+typedef struct tfs_projection_info {
+    int32_t kernel; /* tfs_projection_kernel */
+    int32_t kg, nw; /* systolic: iterations per warp x compute warps (KB = kg*nw fused per pass); red-black: KB, warps per CTA */
+    int32_t passes; /* passes over HBM (two-launch red-black: launches) */
+} tfs_projection_info;
+int tfs_get_last_projection(const tfs_sim *sim, tfs_projection_info *info);
+
+/* Order-independent checksum of the bit patterns of u, v, p, s over this handle's OWNED columns:
+ * out[2f] = wrapping sum, out[2f+1] = xor of per-element 64-bit hashes of (global index, bits), f = u, v,
+ * p, s.  The checksums of the x-slabs of one grid combine (add the sums, xor the xors) to exactly the
+ * single-GPU value, which is how bench.py shows that N GPUs computed the same bits as one.  Synchronises. */
+int tfs_checksum(tfs_sim *sim, uint64_t out[8]);
+
 /* exhaustive device check that the projection's division shortcut equals IEEE x / n for
  * every f32 x and n in {1,2,3,4}; *mismatches must come back 0 */
 int tfs_selftest_division(int device, uint64_t *mismatches);

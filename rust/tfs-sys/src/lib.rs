@@ -30,6 +30,15 @@ pub struct tfs_options {
     pub world: i32,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct tfs_projection_info {
+    pub kernel: i32,
+    pub kg: i32,
+    pub nw: i32,
+    pub passes: i32,
+}
+
 pub const TFS_OK: c_int = 0;
 pub const TFS_ERR_OUT_OF_RANGE: c_int = 2;
 pub const TFS_FIELD_P: c_int = 2;
@@ -59,6 +68,7 @@ extern "C" {
     pub fn tfs_phase_project(sim: *mut tfs_sim, dt: f32) -> c_int;
     pub fn tfs_phase_advect(sim: *mut tfs_sim, dt: f32) -> c_int;
     pub fn tfs_sync(sim: *mut tfs_sim) -> c_int;
+    pub fn tfs_stream_idle(sim: *mut tfs_sim, idle: *mut c_int) -> c_int;
     pub fn tfs_read_view(sim: *mut tfs_sim, field: c_int, x0: usize, y0: usize, w: usize, h: usize, dst: *mut c_void) -> c_int;
     pub fn tfs_read_field(sim: *mut tfs_sim, field: c_int, dst: *mut c_void, n: usize) -> c_int;
     pub fn tfs_write_field(sim: *mut tfs_sim, field: c_int, src: *const c_void, n: usize) -> c_int;
@@ -76,6 +86,8 @@ extern "C" {
     pub fn tfs_set_profiling(sim: *mut tfs_sim, enabled: c_int) -> c_int;
     pub fn tfs_get_phase_ms(sim: *mut tfs_sim, gravity_ms: *mut f32, project_ms: *mut f32, advect_ms: *mut f32, steps: *mut u64) -> c_int;
     pub fn tfs_launch_count(sim: *const tfs_sim, launches: *mut u64) -> c_int;
+    pub fn tfs_get_last_projection(sim: *const tfs_sim, info: *mut tfs_projection_info) -> c_int;
+    pub fn tfs_checksum(sim: *mut tfs_sim, out: *mut u64) -> c_int;
     pub fn tfs_selftest_division(device: c_int, mismatches: *mut u64) -> c_int;
     pub fn tfs_peer_export(sim: *mut tfs_sim, blob: *mut c_void) -> c_int;
     pub fn tfs_peer_attach(sim: *mut tfs_sim, left_blob: *const c_void, right_blob: *const c_void) -> c_int;

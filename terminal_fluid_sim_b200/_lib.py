@@ -21,7 +21,7 @@ SYMBOLS = [
     "tfs_scene_disc", "tfs_scene_lattice", "tfs_scene_random", "tfs_fill_random_velocity",
     "tfs_host_alloc", "tfs_host_free", "tfs_timer_begin", "tfs_timer_end", "tfs_set_profiling",
     "tfs_get_phase_ms", "tfs_launch_count", "tfs_selftest_division", "tfs_peer_export", "tfs_peer_attach",
-    "tfs_slab_bounds", "tfs_get_slab",
+    "tfs_slab_bounds", "tfs_get_slab", "tfs_get_last_projection", "tfs_checksum", "tfs_stream_idle",
 ]
 
 
@@ -34,6 +34,10 @@ class TfsOptions(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("omega", C.c_float), ("mode", C.c_int32),
                 ("device", C.c_int32), ("kernel", C.c_int32), ("temporal_block", C.c_int32),
                 ("rank", C.c_int32), ("world", C.c_int32)]
+
+
+class TfsProjectionInfo(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("kg", C.c_int32), ("nw", C.c_int32), ("passes", C.c_int32)]
 
 
 class TfsError(RuntimeError):
@@ -102,6 +106,9 @@ def load():
     L.tfs_peer_attach.argtypes = [vp, vp, vp]
     L.tfs_slab_bounds.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
     L.tfs_get_slab.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    L.tfs_get_last_projection.argtypes = [vp, C.POINTER(TfsProjectionInfo)]
+    L.tfs_checksum.argtypes = [vp, C.POINTER(u64)]
+    L.tfs_stream_idle.argtypes = [vp, C.POINTER(C.c_int)]
     _lib = L
     return L
 

@@ -16,6 +16,7 @@
 #include "tfs_kernels.cuh"
 #include "tfs_systolic.cuh"
 #include "tfs_systolic4.cuh"
+#include "tfs_redblack.cuh"
 
 #define TFS_VERSION_STRING "tfs-cuda 0.1.0 (sm_100a)"
 
@@ -98,7 +99,13 @@ struct tfs_sim {
     bool attached = false;
     long long step_seq = 0;        // projections run so far (same on every rank)
     bool inkernel_halo = false;    // the last projection kernel delivered the left rank's halo itself (step_slab)
-    int *d_oob = nullptr;          // device flag: an advection sample fell outside the stored columns
+    int *d_oob = nullptr;          // device flag: an advection sample fell outside the columns this rank can reach
+    int *h_oob = nullptr;          // pinned copy, refreshed asynchronously after every slab step
+    cudaEvent_t oob_ev = nullptr;  // recorded after that copy
+    bool oob_pending = false;
+    long long rb_seq = 0;          // red-black passes run so far on a slab handle (same on every rank)
+    unsigned long long *d_sum = nullptr;  // 8 x u64 checksum accumulators
+    tfs_projection_info last_proj{};
 
     tfs::Grid grid() const { return tfs::Grid{(long long)W, (long long)H, xs0, ncols}; }
     long long n() const { return ncols * (long long)H; }          // stored cells
@@ -152,7 +159,7 @@ tfs_sim::Layout slab_layout(long long W, long long H, long long ncols, int b0, i
 
 // indices into the sync area (long long each); all are written by a NEIGHBOUR into this rank's memory
 enum { SYNC_PUSHA_FROM_L = 0, SYNC_PUSHA_FROM_R, SYNC_PUSHB_FROM_L, SYNC_PUSHB_FROM_R, SYNC_ADVDONE_FROM_L, SYNC_ADVDONE_FROM_R,
-       SYNC_PROJDONE_FROM_R };
+       SYNC_PROJDONE_FROM_R, SYNC_RB_FROM_L, SYNC_RB_FROM_R };
 
 struct PeerBlob {
     unsigned magic;
@@ -292,6 +299,14 @@ int check_options(const tfs_options *o) {
     return TFS_OK;
 }
 
+// what an x-slab handle can run (tfs_create and tfs_set_options)
+int check_slab_options(const tfs_options *o) {
+    NEED(o->kernel != TFS_KERNEL_DIAGONAL, TFS_ERR_INVALID_ARG,
+         "x-slab handles run the systolic (exact) or the fused red-black projection, not the diagonal kernel");
+    NEED(o->iterations >= 1, TFS_ERR_INVALID_ARG, "x-slab handles need iterations >= 1");
+    return TFS_OK;
+}
+
 // ---- phases ----------------------------------------------------------------------------------
 
 int phase_gravity(tfs_sim *s, float dt) {
@@ -336,6 +351,58 @@ int project_redblack(tfs_sim *s, float omega, float pc) {
             s->launches++;
         }
     CU(cudaGetLastError());
+    s->last_proj.kernel = TFS_PROJ_REDBLACK_TWO_LAUNCH;
+    s->last_proj.passes = 2 * s->opt.iterations;
+    return TFS_OK;
+}
+
+// the temporally blocked red-black kernel needs an even H (8-byte aligned row pairs); options.kernel == DIAGONAL
+// (or TFS_RB_VARIANT=1) asks for the simple one-launch-per-colour kernel, kept as its on-device cross-check
+bool rb_fused(const tfs_sim *s) {
+    return tfs::redblack_fused_usable((long long)s->W, (long long)s->H, s->ncols) &&
+           (s->slab() || (s->opt.kernel != TFS_KERNEL_DIAGONAL && tunables().rb_variant != 1));
+}
+
+int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq, bool to_left);
+int flags_wait(tfs_sim *s, int idx_from_l, int idx_from_r, long long value);
+
+// Red-black order, temporally blocked: one launch per pass of kRbKB iterations (tfs_redblack.cuh).  On an
+// x-slab handle every pass is followed by a push of the boundary columns of u and v (the pass's output
+// set) into the neighbours' halo columns; the next pass waits for the neighbours' pushes.  `seq` is the
+// step number (slabs only): the first push of a step must wait until both neighbours have finished the
+// previous step's advection, which still reads the halo columns about to be overwritten.
+int project_redblack_fused(tfs_sim *s, float omega, float pc, float gdt, bool fuse_gravity, long long seq) {
+    const int K = s->opt.iterations, KB = tfs::kRbKB;
+    const int passes = (K + KB - 1) / KB;
+    tfs::RbLaunchArgs a{};
+    a.set[0][0] = s->u; a.set[0][1] = s->v; a.set[0][2] = s->p;
+    a.set[1][0] = s->u2; a.set[1][1] = s->v2; a.set[1][2] = s->p2;
+    a.flags = s->flags;
+    a.W = (long long)s->W; a.H = (long long)s->H; a.xs0 = s->xs0; a.ncols = s->ncols; a.c_lo = s->c_lo; a.c_hi = s->c_hi;
+    a.omega = omega; a.pc = pc; a.gdt = gdt; a.apply_gravity = fuse_gravity;
+    a.chunk_len = tunables().rb_chunk;
+    for (int t = 0; t < passes; ++t) {
+        const int k_act = std::min(KB, K - t * KB);
+        cudaError_t e = tfs::redblack_pass(a, t, k_act, s->stream);
+        if (e != cudaSuccess) return fail(TFS_ERR_CUDA, "red-black pass %d: %s", t, cudaGetErrorString(e));
+        s->launches++;
+        if (s->slab()) {
+            int rc;
+            if (t == 0) { rc = flags_wait(s, SYNC_ADVDONE_FROM_L, SYNC_ADVDONE_FROM_R, seq - 1); if (rc) return rc; }
+            const long long rs = ++s->rb_seq;
+            const int out_uv[2] = {(t & 1) ? 0 : 4, (t & 1) ? 1 : 5};  // logical indices of the set pass t wrote
+            rc = halo_push(s, out_uv, 2, SYNC_RB_FROM_R, SYNC_RB_FROM_L, rs, true);
+            if (rc) return rc;
+            rc = flags_wait(s, SYNC_RB_FROM_L, SYNC_RB_FROM_R, rs);
+            if (rc) return rc;
+        }
+    }
+    if (passes & 1) {  // results are in set 1
+        std::swap(s->u, s->u2); std::swap(s->v, s->v2); std::swap(s->p, s->p2);
+        std::swap(s->phys[0], s->phys[4]); std::swap(s->phys[1], s->phys[5]); std::swap(s->phys[2], s->phys[6]);
+    }
+    s->last_proj.kernel = TFS_PROJ_REDBLACK_FUSED;
+    s->last_proj.kg = KB; s->last_proj.nw = 4; s->last_proj.passes = passes;
     return TFS_OK;
 }
 
@@ -351,7 +418,13 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
         CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));
         return TFS_OK;
     }
+    s->last_proj = tfs_projection_info{};
     if (s->opt.mode == TFS_MODE_RED_BLACK) {
+        if (rb_fused(s)) {  // p.fill(0) (:154) is implied: the first pass does not read p
+            int rc2 = project_redblack_fused(s, omega, pc, s->cfg.gravity * dt, fuse_gravity, s->step_seq);
+            if (rc2 == TFS_OK && gravity_done) *gravity_done = fuse_gravity;
+            return rc2;
+        }
         CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));  // :154
         return project_redblack(s, omega, pc);
     }
@@ -419,10 +492,18 @@ int phase_project(tfs_sim *s, float dt, bool fuse_gravity, bool *gravity_done) {
         if (e != cudaSuccess)
             return fail(e == cudaErrorMemoryAllocation ? TFS_ERR_OOM : TFS_ERR_CUDA, "systolic projection: %s (%s)",
                         cudaGetErrorString(e), msg ? msg : "");
+        if (s->sys4.last_kg) {
+            s->last_proj.kernel = TFS_PROJ_SYSTOLIC_BLOCK_RING;
+            s->last_proj.kg = s->sys4.last_kg; s->last_proj.nw = s->sys4.last_nw; s->last_proj.passes = s->sys4.last_passes;
+        } else {
+            s->last_proj.kernel = TFS_PROJ_SYSTOLIC_GENERIC;
+            s->last_proj.kg = s->sys.last_kg; s->last_proj.nw = s->sys.last_nw; s->last_proj.passes = s->sys.last_passes;
+        }
         if (gravity_done) *gravity_done = fuse_gravity;
         return TFS_OK;
     }
     CU(cudaMemsetAsync(s->p, 0, (size_t)s->n() * sizeof(float), s->stream));  // :154
+    s->last_proj.kernel = TFS_PROJ_DIAGONAL;
     return project_diagonal(s, omega, pc);
 }
 
@@ -431,7 +512,7 @@ int phase_advect(tfs_sim *s, float dt) {
     if (rc) return rc;
     tfs::Grid g = s->grid();
     const long long W = (long long)s->W, H = (long long)s->H;
-    const char *adv_env = getenv("TFS_ADVECT");  // tuning aid: "vec4" / "scalar" force the generic kernels
+    const char adv_env = tunables().advect;  // tuning aid: 'v' / 's' force the generic kernels
     // 32-bit cell indices, and W, H < 2^22 for the magic-constant floor of the fast kernels (floor_magic)
     const bool fits32 = W * H < (1LL << 31) - (1LL << 20) && W < (1LL << 22) && H < (1LL << 22);
     const float4 dims = make_float4((float)W, (float)H, (float)(W - 1), (float)(H - 1));
@@ -446,14 +527,24 @@ int phase_advect(tfs_sim *s, float dt) {
     } else if (fits32 && !adv_env) {
         // Two cells per thread with packed f32x2 arithmetic when the rows tile by 256 (k_advect32_pair), else one
         // cell per thread; both ask the L2 for their tile up front when the column segments are 16-byte aligned.
-        static const bool pair = !(getenv("TFS_ADV_PAIR") && atoi(getenv("TFS_ADV_PAIR")) == 0);   // tuning aid
+        const bool pair = tunables().adv_pair;   // tuning aid
         if (pair && H % 256 == 0) {
-            constexpr int CPB = 4;
             auto two = [](float x) { uint32_t b; memcpy(&b, &x, 4); return (tfs::f2)b | ((tfs::f2)b << 32); };
             const tfs::F2K k{two(1.0f), two(-1.0f), two(-0.0f)};
-            dim3 grid((unsigned)(H / 256), blocks_for(W, CPB));
-            tfs::k_advect32_pair<CPB, 8, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W,
-                                                                          (int)H, two(dt), 1.0f, k);
+#define TFS_PAIR_LAUNCH(CPB_, MINB_)                                                                                          \
+    {                                                                                                                        \
+        dim3 grid((unsigned)(H / 256), blocks_for(W, CPB_));                                                                 \
+        tfs::k_advect32_pair<CPB_, MINB_, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, \
+                                                                             (int)W, (int)H, two(dt), 1.0f, k);              \
+    }
+            switch (tunables().adv_variant) {  // experiments; 0 is the shipped configuration
+            case 1: TFS_PAIR_LAUNCH(8, 8) break;
+            case 2: TFS_PAIR_LAUNCH(4, 7) break;
+            case 3: TFS_PAIR_LAUNCH(8, 6) break;
+            case 4: TFS_PAIR_LAUNCH(16, 8) break;
+            default: TFS_PAIR_LAUNCH(4, 8) break;
+            }
+#undef TFS_PAIR_LAUNCH
         } else {
             constexpr int CPB = 8;
             dim3 grid(blocks_for(H, 128), blocks_for(W, CPB));
@@ -464,7 +555,7 @@ int phase_advect(tfs_sim *s, float dt) {
                 tfs::k_advect32<CPB><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W, (int)H, dt,
                                                                   1.0f, dims);
         }
-    } else if (H % 4 == 0 && !(adv_env && adv_env[0] == 's')) {
+    } else if (H % 4 == 0 && adv_env != 's') {
         tfs::k_advect<4><<<blocks_for(W * (H / 4), 256), 256, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2,
                                                                                s->s2, g, 0, W, dt);
     } else {
@@ -485,7 +576,7 @@ int phase_advect(tfs_sim *s, float dt) {
 // ---- x-slab halo exchange ------------------------------------------------------------------------
 // Copy `ncopy` owned boundary columns of the logical fields in `which` into the neighbours' halo
 // columns (peer stores over NVLink), then raise `flag_idx_*` in the neighbours' sync areas to `seq`.
-int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq, bool to_left = true) {
+int halo_push(tfs_sim *s, const int *which, int nwhich, int flag_from_r_idx, int flag_from_l_idx, long long seq, bool to_left) {
     const long long H = (long long)s->H;
     const long long n4 = kHalo * H / 4;
     const unsigned gb = std::min<unsigned>(blocks_for(n4, 256), 148 * 4);
@@ -543,8 +634,11 @@ int flags_signal(tfs_sim *s, int idx_for_left_rank, int idx_for_right_rank, long
 int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
     NEED(s->attached, TFS_ERR_COMM, "x-slab handle: call tfs_peer_attach before stepping");
     NEED(s->opt.iterations > 0, TFS_ERR_INVALID_ARG, "x-slab handles need iterations >= 1");
+    const bool rb = s->opt.mode == TFS_MODE_RED_BLACK;
+    NEED(!rb || rb_fused(s), TFS_ERR_INVALID_ARG, "red-black on x-slabs needs an even height");
     const long long seq = ++s->step_seq;
-    int rc = flags_wait(s, SYNC_PUSHB_FROM_L, -1, seq - 1);
+    // exact mode: the kernel's last band waits for the right rank's pushB itself; red-black reads both halos at once
+    int rc = flags_wait(s, SYNC_PUSHB_FROM_L, rb ? SYNC_PUSHB_FROM_R : -1, seq - 1);
     if (rc) return rc;
     if (ev) CU(cudaEventRecord(ev[1], s->stream));
     bool gravity_done = false;
@@ -553,6 +647,18 @@ int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
     if (!gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
     if (ev) CU(cudaEventRecord(ev[2], s->stream));
     const int uv[2] = {0, 1}, uvs[3] = {0, 1, 3};
+    if (rb) {
+        // every pass already exchanged the boundary columns of u and v (project_redblack_fused), the last one
+        // included, and it waited for advdone(seq-1): the halos are complete
+        rc = phase_advect(s, dt);
+        if (rc) return rc;
+        rc = flags_signal(s, SYNC_ADVDONE_FROM_R, SYNC_ADVDONE_FROM_L, seq);
+        if (rc) return rc;
+        rc = halo_push(s, uvs, 3, SYNC_PUSHB_FROM_R, SYNC_PUSHB_FROM_L, seq, true);
+        if (rc) return rc;
+        if (ev) CU(cudaEventRecord(ev[3], s->stream));
+        return TFS_OK;
+    }
     const bool fine = s->inkernel_halo;
     if (!fine) {
         // The right rank's first band writes the final values of my last KB-1 owned columns (and my first
@@ -580,7 +686,7 @@ int step_slab(tfs_sim *s, float dt, cudaEvent_t *ev) {
     if (rc) return rc;
     rc = flags_signal(s, SYNC_ADVDONE_FROM_R, SYNC_ADVDONE_FROM_L, seq);
     if (rc) return rc;
-    rc = halo_push(s, uvs, 3, SYNC_PUSHB_FROM_R, SYNC_PUSHB_FROM_L, seq);
+    rc = halo_push(s, uvs, 3, SYNC_PUSHB_FROM_R, SYNC_PUSHB_FROM_L, seq, true);
     if (rc) return rc;
     if (ev) CU(cudaEventRecord(ev[3], s->stream));
     return TFS_OK;
@@ -618,6 +724,23 @@ int field_ptr(tfs_sim *s, int field, void **ptr, size_t *elem) {
     case TFS_FIELD_M: *ptr = s->m; *elem = 1; break;
     case TFS_FIELD_FLAGS: *ptr = s->flags; *elem = 1; break;
     default: return fail(TFS_ERR_INVALID_ARG, "field %d is not a tfs_field", field);
+    }
+    return TFS_OK;
+}
+
+// The advection of an x-slab handle flags samples that left the columns it can reach (d_oob).  The flag is
+// copied to pinned memory after every step; `wait` blocks on that copy, otherwise only a finished copy is looked at.
+int check_oob(tfs_sim *s, bool wait) {
+    if (!s->oob_pending) return TFS_OK;
+    if (wait) CU(cudaEventSynchronize(s->oob_ev));
+    else if (cudaEventQuery(s->oob_ev) != cudaSuccess) { cudaGetLastError(); return TFS_OK; }
+    s->oob_pending = false;
+    if (*s->h_oob) {
+        *s->h_oob = 0;
+        cudaMemsetAsync(s->d_oob, 0, sizeof(int), s->stream);
+        return fail(TFS_ERR_OUT_OF_RANGE,
+                    "an advection back-trace left the columns this slab can reach (|velocity|*dt too large for the %lld halo "
+                    "columns and the neighbour slabs); the fields of that step are not valid", kHalo);
     }
     return TFS_OK;
 }
@@ -707,7 +830,7 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
         if (height % 4 != 0) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles need height %% 4 == 0"); }
         if ((long long)width * (long long)height >= (1LL << 31) - (1LL << 20)) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles need width*height < 2^31"); }
         if (s->b0_next >= 0 && s->b0_next <= s->b0) { delete s; return fail(TFS_ERR_INVALID_ARG, "grid too narrow for this many slabs"); }
-        if (o.mode != TFS_MODE_WAVEFRONT_EXACT || o.kernel == TFS_KERNEL_DIAGONAL) { delete s; return fail(TFS_ERR_INVALID_ARG, "x-slab handles run the exact systolic projection only"); }
+        if ((rc = check_slab_options(&o)) != TFS_OK) { delete s; return rc; }
     }
 #define CREATE_TRY(x)         \
     do {                      \
@@ -730,6 +853,9 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
     CREATE_TRY([&]() -> int {
         CU(cudaMalloc((void **)&s->d_oob, sizeof(int)));
         CU(cudaMemsetAsync(s->d_oob, 0, sizeof(int), s->stream));
+        CU(cudaMallocHost((void **)&s->h_oob, sizeof(int)));
+        *s->h_oob = 0;
+        CU(cudaEventCreateWithFlags(&s->oob_ev, cudaEventDisableTiming));
         return TFS_OK;
     }());
     CREATE_TRY(reset_fields(s));
@@ -759,6 +885,9 @@ int tfs_destroy(tfs_sim *s) {
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->d_stage) cudaFree(s->d_stage);
     if (s->d_oob) cudaFree(s->d_oob);
+    if (s->h_oob) cudaFreeHost(s->h_oob);
+    if (s->oob_ev) cudaEventDestroy(s->oob_ev);
+    if (s->d_sum) cudaFree(s->d_sum);
     if (s->peerL.present && s->peerL.ipc) cudaIpcCloseMemHandle(s->peerL.base);
     if (s->peerR.present && s->peerR.ipc) cudaIpcCloseMemHandle(s->peerR.base);
     if (s->prof_created)
@@ -778,29 +907,44 @@ int tfs_resize(tfs_sim *s, size_t width, size_t height) {
     NEED(!s->slab(), TFS_ERR_INVALID_ARG, "resize is not available on x-slab handles (create new handles instead)");
     int rc = set_device(s);
     if (rc) return rc;
-    const size_t n_old = s->W * s->H, n_new = width * height, old_h = s->H;
-    // resize_block_grid (simulator.rs:121-135): clear the old left border, Vec::resize keeps the
-    // FLAT prefix (no (x,y) re-mapping), then set the first new_h entries.
-    uint8_t *m_old = s->m;
-    s->m = nullptr;  // keep across alloc_fields
-    tfs::k_fill_range_u8<<<blocks_for((long long)std::min(old_h, n_old), 256), 256, 0, s->stream>>>(
-        m_old, s->grid(), 0, (long long)std::min(old_h, n_old), 0);
-    s->launches++;
+    const size_t n_old = s->W * s->H, n_new = width * height, old_h = s->H, old_w = s->W, old_cap = s->cap;
+    // Allocate the new arrays first: on failure the handle keeps its old size and fields (the reference's
+    // resize cannot leave the simulator unusable either).
+    float *old_f[8];
+    for (int i = 0; i < 8; ++i) { old_f[i] = logical(s, i); logical(s, i) = nullptr; }
+    uint8_t *m_old = s->m, *flags_old = s->flags;
+    s->m = s->flags = nullptr;
+    const tfs::Grid g_old = s->grid();
     s->W = width;
     s->H = height;
     s->c_lo = 0; s->c_hi = (long long)width; s->xs0 = 0; s->ncols = (long long)width;  // single-GPU handle: the slab is the grid
     rc = alloc_fields(s, n_new);  // zero-fills m
     if (rc) {
-        cudaFree(m_old);
+        free_fields(s);  // whatever part of the new set was allocated
+        for (int i = 0; i < 8; ++i) logical(s, i) = old_f[i];
+        s->m = m_old; s->flags = flags_old; s->cap = old_cap;
+        s->W = old_w; s->H = old_h;
+        s->c_lo = 0; s->c_hi = (long long)old_w; s->xs0 = 0; s->ncols = (long long)old_w;
         return rc;
     }
+    // resize_block_grid (simulator.rs:121-135): clear the old left border, Vec::resize keeps the
+    // FLAT prefix (no (x,y) re-mapping), then set the first new_h entries.
+    tfs::k_fill_range_u8<<<blocks_for((long long)std::min(old_h, n_old), 256), 256, 0, s->stream>>>(
+        m_old, g_old, 0, (long long)std::min(old_h, n_old), 0);
+    s->launches++;
     CU(cudaMemcpyAsync(s->m, m_old, std::min(n_old, n_new), cudaMemcpyDeviceToDevice, s->stream));
     tfs::k_fill_range_u8<<<blocks_for((long long)std::min(height, n_new), 256), 256, 0, s->stream>>>(
         s->m, s->grid(), 0, (long long)std::min(height, n_new), 1);
     s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 8; ++i) cudaFree(old_f[i]);
     cudaFree(m_old);
+    cudaFree(flags_old);
+    // the projection workspaces are laid out for the old size
+    tfs::systolic_release(s->sys);
+    tfs::systolic4_release(s->sys4);
+    for (int i = 0; i < 8; ++i) s->phys[i] = i;
     s->flags_dirty = true;
     rc = reset_fields(s);
     if (rc) return rc;
@@ -813,6 +957,9 @@ int tfs_restart(tfs_sim *s) {
     // the identity and only the left border is rewritten; no reallocation needed.
     int rc = set_device(s);
     if (rc) return rc;
+    CU(cudaMemsetAsync(s->d_oob, 0, sizeof(int), s->stream));
+    if (s->h_oob) *s->h_oob = 0;
+    s->oob_pending = false;
     const long long hh = (long long)std::min(s->H, s->W * s->H);
     tfs::k_fill_range_u8<<<blocks_for(hh, 256), 256, 0, s->stream>>>(s->m, s->grid(), 0, hh, 1);
     s->launches++;
@@ -842,6 +989,10 @@ int tfs_set_options(tfs_sim *s, const tfs_options *opt) {
     if (rc) return rc;
     NEED(opt->device == s->device, TFS_ERR_INVALID_ARG, "the device of a handle cannot change");
     NEED(opt->rank == s->opt.rank && opt->world == s->opt.world, TFS_ERR_INVALID_ARG, "rank/world cannot change");
+    if (s->slab()) {  // the same constraints tfs_create enforces
+        rc = check_slab_options(opt);
+        if (rc) return rc;
+    }
     s->opt = *opt;
     return TFS_OK;
 }
@@ -895,6 +1046,41 @@ int tfs_upload_blocks(tfs_sim *s, const uint8_t *mask, size_t offset, size_t n) 
     return TFS_OK;
 }
 
+namespace {
+int step_body(tfs_sim *s, float dt, cudaEvent_t *ev) {
+    int rc;
+    if (s->slab()) {
+        rc = check_oob(s, false);  // a finished earlier step whose advection overran: report it now
+        if (rc) return rc;
+        rc = step_slab(s, dt, ev);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->h_oob, s->d_oob, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaEventRecord(s->oob_ev, s->stream));
+        s->oob_pending = true;
+        return TFS_OK;
+    }
+    // gravity folds into the first load of v of the systolic and of the fused red-black projection
+    const bool exact = s->opt.mode == TFS_MODE_WAVEFRONT_EXACT;
+    const bool fuse = s->opt.iterations > 0 &&
+                      (exact ? (tfs::systolic_available() && (s->opt.kernel == TFS_KERNEL_AUTO || s->opt.kernel == TFS_KERNEL_SYSTOLIC))
+                             : rb_fused(s));
+    if (!fuse) {
+        rc = phase_gravity(s, dt);
+        if (rc) return rc;
+    }
+    if (ev) CU(cudaEventRecord(ev[1], s->stream));
+    bool gravity_done = false;
+    rc = phase_project(s, dt, fuse, &gravity_done);
+    if (rc) return rc;
+    if (fuse && !gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
+    if (ev) CU(cudaEventRecord(ev[2], s->stream));
+    rc = phase_advect(s, dt);
+    if (rc) return rc;
+    if (ev) CU(cudaEventRecord(ev[3], s->stream));
+    return TFS_OK;
+}
+}  // namespace
+
 int tfs_step(tfs_sim *s, float dt) {
     NEED(s, TFS_ERR_INVALID_ARG, "sim is NULL");
     int rc = set_device(s);
@@ -909,29 +1095,12 @@ int tfs_step(tfs_sim *s, float dt) {
             rc = drain_prof(s);
             if (rc) return rc;
         }
-        ev = s->prof_ev[s->prof_n++];
+        ev = s->prof_ev[s->prof_n];
         CU(cudaEventRecord(ev[0], s->stream));
     }
-    if (s->slab()) return step_slab(s, dt, ev);
-    // gravity folds into the systolic projection's first load of v when that kernel runs
-    const bool exact = s->opt.mode == TFS_MODE_WAVEFRONT_EXACT;
-    const bool want_systolic = exact && tfs::systolic_available() &&
-                               (s->opt.kernel == TFS_KERNEL_AUTO || s->opt.kernel == TFS_KERNEL_SYSTOLIC) &&
-                               s->opt.iterations > 0;
-    if (!want_systolic) {
-        rc = phase_gravity(s, dt);
-        if (rc) return rc;
-    }
-    if (ev) CU(cudaEventRecord(ev[1], s->stream));
-    bool gravity_done = false;
-    rc = phase_project(s, dt, want_systolic, &gravity_done);
-    if (rc) return rc;
-    if (want_systolic && !gravity_done) return fail(TFS_ERR_CUDA, "internal: gravity was not applied");
-    if (ev) CU(cudaEventRecord(ev[2], s->stream));
-    rc = phase_advect(s, dt);
-    if (rc) return rc;
-    if (ev) CU(cudaEventRecord(ev[3], s->stream));
-    return TFS_OK;
+    rc = step_body(s, dt, ev);
+    if (rc == TFS_OK && ev) s->prof_n++;  // a failed step leaves no half-recorded event set behind
+    return rc;
 }
 
 int tfs_phase_gravity(tfs_sim *s, float dt) {
@@ -958,6 +1127,16 @@ int tfs_sync(tfs_sim *s) {
     int rc = set_device(s);
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    return check_oob(s, true);
+}
+
+int tfs_stream_idle(tfs_sim *s, int *idle) {
+    NEED(s && idle, TFS_ERR_INVALID_ARG, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    const cudaError_t e = cudaStreamQuery(s->stream);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(TFS_ERR_CUDA, "cudaStreamQuery: %s", cudaGetErrorString(e));
+    *idle = e == cudaSuccess;
     return TFS_OK;
 }
 
@@ -996,12 +1175,7 @@ int tfs_read_view(tfs_sim *s, int field, size_t x0, size_t y0, size_t w, size_t 
         CU(cudaMemcpyAsync(dst, s->d_stage, w * h * elem, cudaMemcpyDeviceToHost, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
-    {
-        int oob = 0;
-        CU(cudaMemcpy(&oob, s->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
-        if (oob) return fail(TFS_ERR_OUT_OF_RANGE, "an advection back-trace left the slab's %lld halo columns (|velocity|*dt too large)", kHalo);
-    }
-    return TFS_OK;
+    return check_oob(s, true);
 }
 
 // single GPU: the whole field (n = width*height).  x-slab handle: the OWNED columns only
@@ -1206,6 +1380,28 @@ int tfs_launch_count(const tfs_sim *s, uint64_t *launches) {
     NEED(s && launches, TFS_ERR_INVALID_ARG, "NULL argument");
     *launches = s->launches;
     return TFS_OK;
+}
+
+int tfs_get_last_projection(const tfs_sim *s, tfs_projection_info *info) {
+    NEED(s && info, TFS_ERR_INVALID_ARG, "NULL argument");
+    *info = s->last_proj;
+    return TFS_OK;
+}
+
+int tfs_checksum(tfs_sim *s, uint64_t out[8]) {
+    NEED(s && out, TFS_ERR_INVALID_ARG, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    if (!s->d_sum) CU(cudaMalloc((void **)&s->d_sum, 8 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s->d_sum, 0, 8 * sizeof(unsigned long long), s->stream));
+    const long long n = (s->c_hi - s->c_lo) * (long long)s->H;
+    const unsigned gb = (unsigned)std::max<long long>(1, std::min<long long>(blocks_for(n, 256), 148 * 16));
+    tfs::k_checksum<<<gb, 256, 0, s->stream>>>(s->u, s->v, s->p, s->s, s->grid(), s->c_lo - s->xs0, s->c_hi - s->xs0, s->d_sum);
+    s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->d_sum, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return check_oob(s, true);
 }
 
 int tfs_selftest_division(int device, uint64_t *mismatches) {

@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define TFS_DEVINL __device__ __forceinline__
 
@@ -89,4 +90,42 @@ __host__ TFS_DEVINL uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
+}
+
+// Tuning / debugging knobs.  They are environment variables because none is part of
+// the product's interface; they are read ONCE per process, on the first call that needs them (tfs_create),
+// never on the step path.
+struct Tunables {
+    int sys_kg = 0, sys_nw = 0;   // TFS_SYS_KG + TFS_SYS_NW: force a systolic shape
+    int sys_g = 8, sys_rb = 16;   // TFS_SYS_G = 4 / TFS_SYS_RB = 32: record interval / 32-row ring blocks
+    int sys_max_kb = 16;          // TFS_SYS_MAXKB: largest KB the automatic shape choice considers
+    bool sys_v3 = false;          // TFS_SYS_V3 = 1: generic kernel even when H % 4 == 0
+    char sys_order = 0;           // TFS_SYS_ORDER = d / l / h: task order
+    int sys_grid = 0;             // TFS_SYS_GRID = n (cap on resident CTAs), -1 = "even"
+    bool adv_pair = true;         // TFS_ADV_PAIR = 0: one-cell advection kernel
+    char advect = 0;              // TFS_ADVECT = vec4 / scalar: generic advection kernels
+    int adv_variant = 0;          // TFS_ADV_VARIANT = n: experimental advection variants
+    int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
+    int rb_chunk = 0;             // TFS_RB_CHUNK = n: columns per chunk of the fused red-black kernel (0 = default)
+    const char *task_trace_prefix = nullptr;
+};
+inline const Tunables &tunables() {
+    static const Tunables t = [] {
+        Tunables x;
+        auto geti = [](const char *n, int d) { const char *e = getenv(n); return e ? atoi(e) : d; };
+        x.sys_kg = geti("TFS_SYS_KG", 0); x.sys_nw = geti("TFS_SYS_NW", 0);
+        x.sys_g = geti("TFS_SYS_G", 8); x.sys_rb = geti("TFS_SYS_RB", 16);
+        x.sys_max_kb = geti("TFS_SYS_MAXKB", 16);
+        x.sys_v3 = geti("TFS_SYS_V3", 0) != 0;
+        if (const char *e = getenv("TFS_SYS_ORDER")) x.sys_order = e[0];
+        if (const char *e = getenv("TFS_SYS_GRID")) x.sys_grid = e[0] == 'e' ? -1 : atoi(e);
+        x.adv_pair = geti("TFS_ADV_PAIR", 1) != 0;
+        if (const char *e = getenv("TFS_ADVECT")) x.advect = e[0];
+        x.adv_variant = geti("TFS_ADV_VARIANT", 0);
+        x.rb_variant = geti("TFS_RB_VARIANT", 0);
+        x.rb_chunk = geti("TFS_RB_CHUNK", 0);
+        x.task_trace_prefix = getenv("TFS_TASK_TRACE_PREFIX");
+        return x;
+    }();
+    return t;
 }

@@ -665,6 +665,41 @@ __global__ void k_div_partial(const float *__restrict__ u, const float *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Order-independent 64-bit checksum of the bit patterns of u, v, p, s over the columns [c_begin, c_end) of the
+// storage: every element contributes h = splitmix64(global_index << 32 ^ bits) to a wrapping SUM and
+// splitmix64(h) to an XOR, so the pair is exact under any partition of the grid (x-slabs add / xor their
+// shares) and sensitive to where a value sits.  out[2f] += sum, out[2f+1] ^= xor for field f in u, v, p, s.
+__global__ void __launch_bounds__(256) k_checksum(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ p,
+                                                  const float *__restrict__ s, Grid g, long long c_begin, long long c_end,
+                                                  unsigned long long *__restrict__ out) {
+    const float *f[4] = {u, v, p, s};
+    unsigned long long sum[4] = {0, 0, 0, 0}, x[4] = {0, 0, 0, 0};
+    const long long lo = c_begin * g.H, hi = c_end * g.H, shift = g.x0 * g.H;
+    long long t = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; t < hi; t += stride) {
+        const unsigned long long gi = (unsigned long long)(t + shift);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long h = splitmix64((gi << 32) ^ (unsigned long long)__float_as_uint(f[k][t]) ^ ((unsigned long long)k << 62));
+            sum[k] += h;
+            x[k] ^= splitmix64(h);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o; o >>= 1) {
+            sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+            x[k] ^= __shfl_xor_sync(0xffffffffu, x[k], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(out + 2 * k, sum[k]);
+            atomicXor(out + 2 * k + 1, x[k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // view packing: dst[(x-vx0)*vh + (y-vy0)] = src[(x-g.x0)*H + y]  (per-frame D2H staging)
 template <typename T>
 __global__ void k_pack_view(const T *__restrict__ src, T *__restrict__ dst, Grid g, long long vx0,

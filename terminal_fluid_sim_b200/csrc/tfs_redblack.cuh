@@ -1,0 +1,178 @@
+// tfs_redblack.cuh -- make_incompressible in red-black order (TFS_MODE_RED_BLACK), temporally blocked.
+//
+// Same cell update as simulator.rs:161-186, but the sweep order is "all cells with (i + j) even, then all
+// with (i + j) odd" per iteration (cells of one colour touch disjoint faces).  The result is bit-identical
+// to the oracle's own statement of that order (orc_make_incompressible_redblack); against the reference's
+// lexicographic order it is compared under the measured tolerance stated in tests/test_gpu_parity.py.
+//
+// One PASS fuses KB iterations (2*KB half-sweeps = "stages") and is one kernel launch; passes ping-pong
+// between the two (u, v, p) buffer sets like the systolic kernel, so HBM sees ~(13 r + 12 w)/KB bytes per
+// cell-iteration instead of >= 42 for one launch per colour.
+//
+//   * a WARP owns a strip of 64 rows; lane l holds the row pair (j0 + 2l, j0 + 2l + 1) -- one cell of each
+//     colour per column -- so every lane has exactly one active cell per column and half-sweep, and which
+//     of the two it is is known at compile time (column parity);
+//   * the warp marches in +x holding a window of NS = 2*KB columns in REGISTERS.  At march step x stage s
+//     (half-sweep s of the pass) updates column x-1-s: its four neighbours were brought to half-sweep s-1 by
+//     stage s-1 earlier in the same step (column x-s), two steps ago (column x-2-s) or one step ago (the
+//     rows above / below, same column) -- a software pipeline over the half-sweeps with no synchronisation
+//     between warps at all.  Column x-NS leaves the window final after step x;
+//   * vertical neighbours inside the strip are a register of the same lane (pair partner) or of lane l+1
+//     (two shuffles per upper-row update: fetch v[top], hand the updated value back);
+//   * strips and column chunks OVERLAP by NS rows / columns and recompute the overlap: a wrong value at the
+//     edge of what was loaded moves inwards by at most one cell per half-sweep, so after NS stages the
+//     inner 64 - 2*NS rows and Lx columns are exact.  No halo exchange, no cross-CTA dependency, and the
+//     same kernel serves x-slabs (the slab's NS stored halo columns are the chunk overlap).
+//   * warp-uniform fast path when every cell of a column's 64 rows is plain interior fluid (11 flops/cell).
+#pragma once
+#include "tfs_systolic.cuh"  // cell_update4
+
+namespace tfs {
+
+struct RbParams {
+    const float *in_u, *in_v, *in_p;  // set read by this pass (storage pointers: column xs0 first)
+    float *out_u, *out_v, *out_p;     // set written by this pass
+    const uint8_t *flags;
+    int W, H;            // global grid
+    int xs0, ncols;      // stored columns [xs0, xs0 + ncols)
+    int c_lo, c_hi;      // owned columns: the ones this launch writes
+    int n_strips;        // strips of V = 64 - 2*NS rows
+    int chunk0, lx;      // first column chunk (global index), chunk length (multiple of NS)
+    int ns_act;          // active stages of this pass (2 * iterations fused in it)
+    int apply_gravity;   // first pass: v += gdt on updatable cells while loading (simulator.rs:137-149)
+    float omega, pc, gdt;
+};
+
+template <int KB, bool FIRST>
+__global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
+    constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
+    constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
+    static_assert(V >= 8, "too many fused iterations for a 64-row strip");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * 4 + warp;
+    if (strip >= P.n_strips) return;
+    const int H = P.H, xs0 = P.xs0, ncols = P.ncols;
+    const int rA = strip * V - NS + 2 * lane;             // lower row of this lane's pair (even)
+    const bool row_ok = rA >= 0 && rA < H;                // H is even: the pair is inside or outside together
+    const bool store_lane = row_ok && lane >= KB && lane < 32 - KB;
+    const int gx0 = (P.chunk0 + (int)blockIdx.y) * P.lx;  // first column this chunk finalises
+    const int vx0 = max(gx0, P.c_lo), vx1 = min(gx0 + P.lx, P.c_hi);
+    const int ns_act = P.ns_act;
+    const float omega = P.omega, pc = P.pc;
+
+    // register window: slot c holds column i with i % NS == c (rows A = lower, B = upper)
+    float uA[NS], uB[NS], vA[NS], vB[NS], pA[NS], pB[NS];
+    unsigned fl[NS];      // flag bytes: A | B << 8
+    unsigned plain = 0u;  // bit c: all 64 cells of slot c are plain interior fluid (warp-uniform)
+#pragma unroll
+    for (int c = 0; c < NS; ++c) { uA[c] = uB[c] = vA[c] = vB[c] = pA[c] = pB[c] = 0.0f; fl[c] = 0u; }
+
+    struct Col { float2 u, v, p; unsigned f; };
+    auto load_col = [&](int i) -> Col {
+        Col r;
+        r.u = r.v = r.p = make_float2(0.0f, 0.0f);
+        r.f = 0u;
+        const int li = i - xs0;
+        if (row_ok && (unsigned)li < (unsigned)ncols) {  // stored columns lie inside the grid
+            const size_t o = (size_t)li * (size_t)H + (size_t)rA;
+            r.u = __ldg(reinterpret_cast<const float2 *>(P.in_u + o));
+            r.v = __ldg(reinterpret_cast<const float2 *>(P.in_v + o));
+            if (!FIRST) r.p = __ldg(reinterpret_cast<const float2 *>(P.in_p + o));
+            r.f = __ldg(reinterpret_cast<const unsigned short *>(P.flags + o));
+            if (FIRST && P.apply_gravity) {
+                if (r.f & TFS_F_LIVE) r.v.x = fadd(r.v.x, P.gdt);
+                if ((r.f >> 8) & TFS_F_LIVE) r.v.y = fadd(r.v.y, P.gdt);
+            }
+        }
+        return r;
+    };
+
+    int x = gx0 - NS;          // newest column held (the "pending" one): stage s works on column x-1-s
+    Col pend = load_col(x);    // its u is the right face of column x-1; v, p, flags wait for the next step
+    const int n_it = (P.lx + 2 * NS) / NS;
+    for (int it = 0; it < n_it; ++it) {
+#pragma unroll
+        for (int m = 0; m < NS; ++m, ++x) {  // x % NS == m, x % 2 == m % 2
+            const Col nxt = load_col(x + 1);  // consumed at the end of this step
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if (s < ns_act) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int c = (m - 1 - s + 2 * NS) % NS;  // slot of column x-1-s
+                    const int cn = (c + 1) % NS;              // slot of column x-s (s == 0: the pending column)
+                    // colour of the half-sweep = s & 1; the lower cell (even row) of column i is active when
+                    // (i & 1) == (s & 1), i.e. when m is odd -- a compile-time fact
+                    const bool lower = (m & 1) != 0;
+                    const bool is_plain = (plain >> c) & 1u;
+                    if (lower) {
+                        float &uR = (s == 0) ? pend.u.x : uA[cn];
+                        if (is_plain) cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                        else cell_update4<2>(fl[c] & 15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                    } else {
+                        float &uR = (s == 0) ? pend.u.y : uB[cn];
+                        float vT = __shfl_down_sync(0xffffffffu, vA[c], 1);  // lane 31: its own value, inside the overlap
+                        if (is_plain) cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
+                        else cell_update4<2>((fl[c] >> 8) & 15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
+                        vT = __shfl_up_sync(0xffffffffu, vT, 1);
+                        if (lane > 0) vA[c] = vT;
+                    }
+                }
+            }
+            // column x-NS (slot m) has seen all NS stages: store its exact part, then the slot takes column x
+            {
+                const int i = x - NS;
+                if (store_lane && i >= vx0 && i < vx1) {
+                    const size_t o = (size_t)(i - xs0) * (size_t)H + (size_t)rA;
+                    *reinterpret_cast<float2 *>(P.out_u + o) = make_float2(uA[m], uB[m]);
+                    *reinterpret_cast<float2 *>(P.out_v + o) = make_float2(vA[m], vB[m]);
+                    *reinterpret_cast<float2 *>(P.out_p + o) = make_float2(pA[m], pB[m]);
+                }
+                uA[m] = pend.u.x; uB[m] = pend.u.y; vA[m] = pend.v.x; vB[m] = pend.v.y; pA[m] = pend.p.x; pB[m] = pend.p.y;
+                fl[m] = pend.f;
+                const bool pl = __all_sync(0xffffffffu, pend.f == 0x1F1Fu);
+                plain = (plain & ~(1u << m)) | ((pl ? 1u : 0u) << m);
+                pend = nxt;
+            }
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+constexpr int kRbKB = 4;  // iterations fused per pass: 8 window columns, 48 exact rows per 64-row strip
+
+struct RbLaunchArgs {
+    float *set[2][3];      // [set][u, v, p]; pass t reads set t & 1 and writes the other
+    const uint8_t *flags;
+    long long W, H, xs0, ncols, c_lo, c_hi;
+    float omega, pc, gdt;
+    bool apply_gravity;
+    int chunk_len;         // 0 = default
+};
+
+inline bool redblack_fused_usable(long long W, long long H, long long ncols) {
+    return (H % 2) == 0 && W < (1LL << 30) && H < (1LL << 30) && ncols < (1LL << 30);
+}
+
+// one pass (iterations [kb*t, kb*t + k_act)) of the fused red-black projection
+inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaStream_t stream) {
+    constexpr int KB = kRbKB, NS = 2 * KB, V = 64 - 2 * NS;
+    RbParams P{};
+    const int in = t & 1, out = in ^ 1;
+    P.in_u = a.set[in][0]; P.in_v = a.set[in][1]; P.in_p = a.set[in][2];
+    P.out_u = a.set[out][0]; P.out_v = a.set[out][1]; P.out_p = a.set[out][2];
+    P.flags = a.flags;
+    P.W = (int)a.W; P.H = (int)a.H; P.xs0 = (int)a.xs0; P.ncols = (int)a.ncols; P.c_lo = (int)a.c_lo; P.c_hi = (int)a.c_hi;
+    P.n_strips = (int)((a.H + V - 1) / V);
+    P.lx = a.chunk_len > 0 ? (a.chunk_len + NS - 1) / NS * NS : 128;
+    P.chunk0 = (int)(a.c_lo / P.lx);
+    const int n_chunks = (int)((a.c_hi + P.lx - 1) / P.lx) - P.chunk0;
+    P.ns_act = 2 * k_act;
+    P.apply_gravity = (t == 0 && a.apply_gravity) ? 1 : 0;
+    P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
+    dim3 grid((unsigned)((P.n_strips + 3) / 4), (unsigned)n_chunks);
+    if (t == 0) k_project_rb<KB, true><<<grid, 128, 0, stream>>>(P);
+    else k_project_rb<KB, false><<<grid, 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace tfs

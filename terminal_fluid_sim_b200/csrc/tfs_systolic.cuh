@@ -38,6 +38,7 @@ struct SystolicWorkspace {
     void *buf = nullptr;  // records + counters
     size_t bytes = 0;
     int num_sms = 0;
+    int last_kg = 0, last_nw = 0, last_passes = 0;  // shape of the last generic-kernel launch
 };
 
 struct SystolicArgs {
@@ -602,6 +603,7 @@ struct SysLaunch {
         kern<<<grid, 32 * (NW + 1), smem, a.stream>>>(P);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
+        ws.last_kg = KG; ws.last_nw = NW; ws.last_passes = P.n_passes;
 #ifdef TFS_SYS_TRACE
         {
             long long h[64 * 8];
@@ -634,30 +636,36 @@ struct SysLaunch {
 
 inline bool systolic_available() { return true; }
 
-// (KG, NW) shapes that are instantiated; KB = KG*NW iterations are fused per pass.
-struct SysShape { int kg, nw; };
+// (KG, NW) shapes; KB = KG*NW iterations are fused per pass.  v3: instantiated for the generic kernel below
+// (any H), v4: for the block-ring kernel of tfs_systolic4.cuh (H % 4 == 0).  A shape is only ever picked for
+// the kernel family that has it, so the family never changes silently with the iteration count.
+struct SysShape { int kg, nw; bool v3, v4; };
 inline const SysShape *systolic_shapes(int *n) {
-    static const SysShape shapes[] = {{4, 4}, {6, 4}, {4, 8}, {4, 3}, {2, 5}, {4, 2}, {2, 8}, {2, 4}, {2, 2}, {5, 2}, {1, 8}, {8, 2}, {8, 4}, {8, 1}};
+    static const SysShape shapes[] = {{4, 4, true, true},  {5, 4, false, true}, {6, 4, false, true}, {4, 8, true, true},
+                                      {4, 3, true, true},  {2, 5, true, true},  {4, 2, true, true},  {2, 8, true, true},
+                                      {2, 4, true, true},  {2, 2, true, true},  {5, 2, true, true},  {1, 8, true, true},
+                                      {8, 2, false, true}, {8, 4, false, true}, {8, 1, false, true}};
     *n = (int)(sizeof(shapes) / sizeof(shapes[0]));
     return shapes;
 }
 
 // choose the shape: an explicit temporal_block picks the first shape with that KB (else the
 // largest KB below it); auto minimises passes * (KB + overhead) so the last pass wastes little.
-inline SysShape systolic_pick(int iterations, int requested) {
+inline SysShape systolic_pick(int iterations, int requested, bool v4_only) {
     int n = 0;
     const SysShape *sh = systolic_shapes(&n);
-    const char *env_kg = getenv("TFS_SYS_KG"), *env_nw = getenv("TFS_SYS_NW");
-    if (env_kg && env_nw) {
+    auto has = [&](const SysShape &x) { return v4_only ? x.v4 : x.v3; };
+    const Tunables &tn = tunables();
+    if (tn.sys_kg && tn.sys_nw) {
         for (int i = 0; i < n; ++i)
-            if (sh[i].kg == atoi(env_kg) && sh[i].nw == atoi(env_nw)) return sh[i];
+            if (sh[i].kg == tn.sys_kg && sh[i].nw == tn.sys_nw && has(sh[i])) return sh[i];
     }
     if (requested > 0) {
-        SysShape best = {2, 2};
+        SysShape best = {2, 2, true, true};
         int best_kb = 0;
         for (int i = 0; i < n; ++i) {
             const int kb = sh[i].kg * sh[i].nw;
-            if (kb <= requested && kb > best_kb) { best_kb = kb; best = sh[i]; }
+            if (has(sh[i]) && kb <= requested && kb > best_kb) { best_kb = kb; best = sh[i]; }
         }
         return best;
     }
@@ -665,7 +673,7 @@ inline SysShape systolic_pick(int iterations, int requested) {
     double best_cost = 1e30;
     for (int i = 0; i < n; ++i) {
         const int kb = sh[i].kg * sh[i].nw;
-        if (kb > 16 || sh[i].nw > 4) continue;  // measured on B200: (4,4) with 16-row rings (3 CTAs/SM) wins or ties at every K tried
+        if (!has(sh[i]) || kb > tn.sys_max_kb || sh[i].nw > 4) continue;  // measured on B200: 3 CTAs/SM shapes win or tie at every K tried
         const int passes = (iterations + kb - 1) / kb;
         const double cost = passes * (kb + 16.0);  // measured on B200: a pass costs ~16 iterations' worth of fixed latency
         if (cost < best_cost - 1e-9) { best_cost = cost; best = sh[i]; }
@@ -674,14 +682,8 @@ inline SysShape systolic_pick(int iterations, int requested) {
 }
 
 inline cudaError_t systolic_project(const SystolicArgs &a, SystolicWorkspace &ws, uint64_t *launched, const char **msg) {
-    const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
-    const char *env_s = getenv("TFS_SYS_S");
-    const int S_ = env_s ? atoi(env_s) : 16;
-    if (S_ == 8 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 8, 6>::run(a, ws, launched, msg);
-    if (S_ == 8 && sh.kg == 2 && sh.nw == 8) return SysLaunch<2, 8, 8, 6>::run(a, ws, launched, msg);
-    if (S_ == 32 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 32, 6>::run(a, ws, launched, msg);
-    if (S_ == 64 && sh.kg == 4 && sh.nw == 4) return SysLaunch<4, 4, 64, 6>::run(a, ws, launched, msg);
-    if (S_ == 64 && sh.kg == 1 && sh.nw == 8) return SysLaunch<1, 8, 64, 6>::run(a, ws, launched, msg);
+    ws.last_kg = ws.last_nw = ws.last_passes = 0;
+    const SysShape sh = systolic_pick(a.iterations, a.temporal_block, false);
 #define TFS_SYS_CASE(KG_, NW_) \
     if (sh.kg == KG_ && sh.nw == NW_) return SysLaunch<KG_, NW_, 16, 6>::run(a, ws, launched, msg);
     TFS_SYS_CASE(4, 4)
@@ -695,7 +697,8 @@ inline cudaError_t systolic_project(const SystolicArgs &a, SystolicWorkspace &ws
     TFS_SYS_CASE(4, 8)
     TFS_SYS_CASE(1, 8)
 #undef TFS_SYS_CASE
-    return SysLaunch<4, 4, 16, 6>::run(a, ws, launched, msg);  // shape only built for the block-ring kernel
+    *msg = "internal: systolic_pick returned a shape without a generic-kernel instantiation";
+    return cudaErrorInvalidValue;
 }
 
 inline void systolic_release(SystolicWorkspace &ws) {

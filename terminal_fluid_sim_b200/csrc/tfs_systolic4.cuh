@@ -117,7 +117,7 @@ struct Sys4Smem {
 };
 
 template <int KG, int NW, int G, int RB>
-__global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 4) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
+__global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
     using SM = Sys4Smem<KG, NW, G, RB>;
     static_assert(RB == 16 || RB == 32, "ring blocks are 16 or 32 rows");
     static_assert(RB % G == 0, "a ring block is a whole number of record intervals");
@@ -643,6 +643,7 @@ struct Systolic4Workspace {
     long long key_W = -1, key_H = -1;
     int key_passes = -1, key_bands = -1, key_b0 = -1, key_nbl = -1, key_kb = -1;
     long long seq = 0;
+    int last_kg = 0, last_nw = 0, last_passes = 0;  // shape of the last launch (tfs_get_last_projection)
 };
 
 template <int KG, int NW, int G, int RB>
@@ -685,11 +686,15 @@ struct Sys4Launch {
                 ws.buf = nullptr;
                 ws.bytes = 0;
                 if ((e = cudaMalloc(&ws.buf, need)) != cudaSuccess) { *msg = "workspace allocation"; return e; }
-                if ((e = cudaMemsetAsync(ws.buf, 0, need, a.stream)) != cudaSuccess) return e;  // counters start below any seq
                 ws.bytes = need;
             }
             P.bnd = reinterpret_cast<float4 *>(ws.buf);
             P4.bnd_prog64 = reinterpret_cast<long long *>(reinterpret_cast<char *>(ws.buf) + rec_bytes);
+            // The counters' position depends on (W, H, shape, passes) and the buffer is shared with the record
+            // streams and with the generic kernel, so whatever lies there now may be stale records of another
+            // layout: zero them on every launch (a few hundred KB at most; the slab path keeps fixed offsets and
+            // relies on `seq` instead, because a neighbour may publish before this rank launches).
+            if ((e = cudaMemsetAsync(P4.bnd_prog64, 0, n_cnt * sizeof(long long) + 64, a.stream)) != cudaSuccess) return e;
             P4.out_prog64 = P4.bnd_prog64 + (size_t)P.n_passes * P4.cstride;
             P.ticket = reinterpret_cast<int *>(P4.out_prog64 + (size_t)P.n_passes * P4.cstride);
         } else {
@@ -740,7 +745,7 @@ struct Sys4Launch {
         // key, on this rank and on its neighbours alike.
         const long long n_tasks = (long long)P.n_passes * SL.nb_local;
         if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands ||
-            ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB || getenv("TFS_SYS_ORDER")) {
+            ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB) {
             if (ws4.n_tasks_cap < (size_t)n_tasks) {
                 if (ws4.d_tasks) cudaFree(ws4.d_tasks);
                 if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
@@ -757,11 +762,11 @@ struct Sys4Launch {
             int lag_b = 32 + 2 * G, lag_t = 2 * lag_b + 64 + KB;  // lag_t > lag_b: (b+1, tb-1) sorts before (b, tb)
             bool hybrid = false;  // pass 0 first (feeds the next rank's bands), later passes in start-time order
             {
-                const char *ord = getenv("TFS_SYS_ORDER");
-                const long long slots = (long long)ws.num_sms * 2;
+                const char ord = tunables().sys_order;
+                const long long slots = (long long)ws.num_sms * 3;  // resident CTAs of the shipped shapes
                 // measured on 8 B200 at 32768^2, K=200: pass-major 190 ms/step, hybrid 505, start-time 524
-                const bool lex = ord ? (ord[0] == 'l') : (ext != nullptr && n_tasks > slots);
-                hybrid = ord ? (ord[0] == 'h') : false;
+                const bool lex = ord ? (ord == 'l') : (ext != nullptr && n_tasks > slots);
+                hybrid = ord == 'h';
                 if (lex) lag_t = 1 << 24;
             }
             std::vector<std::pair<long long, int2>> v;
@@ -794,11 +799,11 @@ struct Sys4Launch {
         const int occ = occ_dev[di];
         if (occ < 1) { *msg = "kernel does not fit on an SM"; return cudaErrorLaunchOutOfResources; }
         int grid = (int)std::min<long long>(n_tasks, (long long)occ * ws.num_sms);
-        if (const char *ge = getenv("TFS_SYS_GRID")) {  // tuning aid: "even" = whole rounds, or a CTA count
-            if (ge[0] == 'e') {
+        if (const int ge = tunables().sys_grid) {  // tuning aid: -1 ("even") = whole rounds, or a CTA count
+            if (ge < 0) {
                 const long long rounds = (n_tasks + grid - 1) / grid;
                 grid = (int)((n_tasks + rounds - 1) / rounds);
-            } else if (atoi(ge) > 0) grid = std::min(grid, atoi(ge));
+            } else grid = std::min(grid, ge);
         }
 #ifdef TFS_SYS_TRACE
         static long long *d_trace = nullptr;
@@ -821,8 +826,9 @@ struct Sys4Launch {
         kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
+        ws4.last_kg = KG; ws4.last_nw = NW; ws4.last_passes = P.n_passes;
 #ifdef TFS_TASK_TRACE
-        if (const char *pre = getenv("TFS_TASK_TRACE_PREFIX")) {
+        if (const char *pre = tunables().task_trace_prefix) {
             cudaStreamSynchronize(a.stream);
             std::vector<unsigned long long> h((size_t)n_tasks * 4);
             cudaMemcpy(h.data(), d_tt[di], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -873,42 +879,44 @@ inline void systolic4_release(Systolic4Workspace &ws4) {
 }
 
 // The block-ring kernel needs H % 4 == 0 (16-byte column alignment); otherwise the generic cp.async-4
-// kernel of tfs_systolic.cuh runs (single GPU only).
-inline bool systolic4_usable(const SystolicArgs &a) {
-    const char *force_v3 = getenv("TFS_SYS_V3");
-    return (a.H % 4) == 0 && !(force_v3 && atoi(force_v3));
-}
+// kernel of tfs_systolic.cuh runs (single GPU only).  The choice depends on H alone, never on the iteration
+// count: every shape systolic_pick can return for v4_only has a case below.
+inline bool systolic4_usable(const SystolicArgs &a) { return (a.H % 4) == 0 && !tunables().sys_v3; }
 
 inline cudaError_t systolic_project_auto(const SystolicArgs &a, const Sys4External *ext, SystolicWorkspace &ws,
                                          Systolic4Workspace &ws4, uint64_t *launched, const char **msg) {
+    ws4.last_kg = ws4.last_nw = ws4.last_passes = 0;
     if (!systolic4_usable(a)) {
         if (ext) { *msg = "x-slab handles need H % 4 == 0"; return cudaErrorInvalidValue; }
         return systolic_project(a, ws, launched, msg);
     }
-    const SysShape sh = systolic_pick(a.iterations, a.temporal_block);
-    const char *env_g = getenv("TFS_SYS_G"), *env_rb = getenv("TFS_SYS_RB");
-    const int G_ = env_g ? atoi(env_g) : 8;
-    const int RB_ = env_rb ? atoi(env_rb) : 16;
-#define TFS_SYS4_CASE(KG_, NW_)                                                                          \
-    if (sh.kg == KG_ && sh.nw == NW_) {                                                                  \
-        if (RB_ == 16 && G_ != 4) return Sys4Launch<KG_, NW_, 8, 16>::run(a, ext, ws, ws4, launched, msg);   \
-        if (G_ == 4) return Sys4Launch<KG_, NW_, 4, 32>::run(a, ext, ws, ws4, launched, msg);            \
-        return Sys4Launch<KG_, NW_, 8, 32>::run(a, ext, ws, ws4, launched, msg);                         \
+    const SysShape sh = systolic_pick(a.iterations, a.temporal_block, true);
+    const int G_ = tunables().sys_g, RB_ = tunables().sys_rb;
+    // the 32-row-ring / G = 4 variants are tuning aids, built for the default shape only
+    if (sh.kg == 4 && sh.nw == 4 && (RB_ != 16 || G_ == 4)) {
+        if (G_ == 4) return Sys4Launch<4, 4, 4, 32>::run(a, ext, ws, ws4, launched, msg);
+        return Sys4Launch<4, 4, 8, 32>::run(a, ext, ws, ws4, launched, msg);
     }
+#define TFS_SYS4_CASE(KG_, NW_) \
+    if (sh.kg == KG_ && sh.nw == NW_) return Sys4Launch<KG_, NW_, 8, 16>::run(a, ext, ws, ws4, launched, msg);
+    TFS_SYS4_CASE(4, 4)
+    TFS_SYS4_CASE(5, 4)
     TFS_SYS4_CASE(6, 4)
     TFS_SYS4_CASE(4, 8)
-    TFS_SYS4_CASE(4, 4)
     TFS_SYS4_CASE(4, 3)
     TFS_SYS4_CASE(2, 5)
     TFS_SYS4_CASE(4, 2)
     TFS_SYS4_CASE(2, 8)
     TFS_SYS4_CASE(2, 4)
+    TFS_SYS4_CASE(2, 2)
+    TFS_SYS4_CASE(5, 2)
+    TFS_SYS4_CASE(1, 8)
     TFS_SYS4_CASE(8, 2)
     TFS_SYS4_CASE(8, 4)
     TFS_SYS4_CASE(8, 1)
 #undef TFS_SYS4_CASE
-    if (ext) return Sys4Launch<4, 4, 8, 32>::run(a, ext, ws, ws4, launched, msg);
-    return systolic_project(a, ws, launched, msg);
+    *msg = "internal: systolic_pick returned a shape without a block-ring instantiation";
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace tfs

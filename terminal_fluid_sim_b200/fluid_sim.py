@@ -15,11 +15,13 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import TfsConfig, TfsError, TfsOptions, check
+from ._lib import TfsConfig, TfsError, TfsOptions, TfsProjectionInfo, check
 
 MODE_WAVEFRONT_EXACT, MODE_RED_BLACK = 0, 1
 KERNEL_AUTO, KERNEL_SYSTOLIC, KERNEL_DIAGONAL = 0, 1, 2
 FIELD_U, FIELD_V, FIELD_P, FIELD_S, FIELD_M, FIELD_FLAGS = range(6)
+(PROJ_NONE, PROJ_SYSTOLIC_BLOCK_RING, PROJ_SYSTOLIC_GENERIC, PROJ_DIAGONAL, PROJ_REDBLACK_FUSED,
+ PROJ_REDBLACK_TWO_LAUNCH) = range(6)
 
 
 @dataclass
@@ -133,6 +135,12 @@ class FluidSim:
     def sync(self):
         check(self._L.tfs_sync(self._h))
 
+    def idle(self) -> bool:
+        """non-blocking: has everything enqueued so far finished?"""
+        i = C.c_int()
+        check(self._L.tfs_stream_idle(self._h, C.byref(i)))
+        return bool(i.value)
+
     def phase_gravity(self, dt):
         check(self._L.tfs_phase_gravity(self._h, dt))
 
@@ -203,6 +211,19 @@ class FluidSim:
         mn, mx = C.c_float(), C.c_float()
         check(self._L.tfs_render_view(self._h, x0, area_w, area_h, mm, out.ctypes.data, C.byref(mn), C.byref(mx)))
         return out, mn.value, mx.value
+
+    def last_projection(self) -> dict:
+        """kernel (PROJ_*) and shape of the projection the last step ran"""
+        i = TfsProjectionInfo()
+        check(self._L.tfs_get_last_projection(self._h, C.byref(i)))
+        return {"kernel": i.kernel, "kg": i.kg, "nw": i.nw, "passes": i.passes}
+
+    def checksum(self) -> np.ndarray:
+        """8 x u64: (wrapping sum, xor) of per-element hashes of u, v, p, s over the OWNED columns;
+        x-slab shares combine with `combine_checksums`"""
+        out = (C.c_uint64 * 8)()
+        check(self._L.tfs_checksum(self._h, out))
+        return np.array(list(out), dtype=np.uint64)
 
     def divergence_linf(self) -> float:
         r = C.c_float()
@@ -292,6 +313,36 @@ class PinnedBuffer:
             pass
 
 
+def combine_checksums(parts) -> np.ndarray:
+    """checksum of the whole grid from the checksums of its x-slabs (sums add mod 2^64, xors xor)"""
+    out = np.zeros(8, np.uint64)
+    for p in parts:
+        p = np.asarray(p, np.uint64)
+        with np.errstate(over="ignore"):
+            out[0::2] = out[0::2] + p[0::2]
+        out[1::2] ^= p[1::2]
+    return out
+
+
+def checksum_of_fields(u, v, p, s) -> np.ndarray:
+    """the same checksum computed on the host from whole-grid arrays (the oracle's fields, in tests)"""
+    def sm64(x):
+        with np.errstate(over="ignore"):
+            x = x + np.uint64(0x9E3779B97F4A7C15)
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    out = np.zeros(8, np.uint64)
+    for k, f in enumerate((u, v, p, s)):
+        bits = np.ascontiguousarray(f, np.float32).view(np.uint32).astype(np.uint64)
+        gi = np.arange(bits.size, dtype=np.uint64)
+        h = sm64((gi << np.uint64(32)) ^ bits ^ (np.uint64(k) << np.uint64(62)))
+        with np.errstate(over="ignore"):
+            out[2 * k] = np.add.reduce(h, dtype=np.uint64)
+        out[2 * k + 1] = np.bitwise_xor.reduce(sm64(h))
+    return out
+
+
 def selftest_division(device: int = 0) -> int:
     n = C.c_uint64()
     check(_lib.load().tfs_selftest_division(device, C.byref(n)))
@@ -324,11 +375,22 @@ class SlabGroup:
     def next_step(self, dt):
         self.each("next_step", dt)
 
-    def sync(self):
+    def sync(self, timeout_s: float | None = None):
+        """wait for every slab; with a timeout the wait polls and raises TimeoutError instead of blocking forever"""
+        if timeout_s is not None:
+            import time
+            t0 = time.time()
+            while not all(s.idle() for s in self.sims):
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError("x-slab step did not finish in %.0f s" % timeout_s)
+                time.sleep(0.002)
         self.each("sync")
 
     def read_field(self, field):
         return np.concatenate([s.read_field(field) for s in self.sims])
+
+    def checksum(self):
+        return combine_checksums([s.checksum() for s in self.sims])
 
     def close(self):
         self.each("close")

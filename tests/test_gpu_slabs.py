@@ -81,6 +81,34 @@ def test_config4_like_lattice_slabs_equal_single_gpu_bitwise(world):
     one.close(); grp.close()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("W,H,K,g", [(256, 64, 4, 0.0), (520, 96, 50, 9.8), (1024, 256, 41, 0.0)])
+def test_redblack_slabs_match_oracle_bit_exact(world, W, H, K, g):
+    """red-black mode on x-slabs: every pass exchanges the 8 boundary columns of u and v with the neighbours"""
+    if _ndev() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if (W + 1 + 31) // 32 < world:
+        pytest.skip("grid too narrow for this many slabs")
+    grp = tfs.SlabGroup(W, H, tfs.SimConfig(gravity=g), world=world, iterations=K, mode=tfs.MODE_RED_BLACK)
+    o = OracleSim(W, H, gravity=g, iterations=K, mode=1)
+    thr = frac_to_threshold(0.05)
+    grp.each("scene_random", 77, thr); o.L.orc_scene_random(o.h, 77, thr)
+    grp.each("fill_random_velocity", 5, 60.0); o.fill_random_velocity(5, 60.0)
+    for st in range(3):
+        grp.next_step(DT); o.step(DT)
+        grp.sync()
+        for f, n in FIELDS:
+            a, b = grp.read_field(f), getattr(o, n)
+            assert bits_equal(a, b), f"world={world} step {st} {n}: " + first_mismatch(a, b, H)
+    for _ in range(4):                                        # back to back, ordered by the device-side flags only
+        grp.next_step(DT); o.step(DT)
+    grp.sync()
+    for f, n in FIELDS:
+        assert bits_equal(grp.read_field(f), getattr(o, n)), n
+    assert np.array_equal(grp.checksum(), tfs.checksum_of_fields(o.u, o.v, o.p, o.s))
+    grp.close()
+
+
 def test_slab_handle_rejects_what_it_cannot_do():
     if _ndev() < 2:
         pytest.skip("needs 2 GPUs")
@@ -93,4 +121,10 @@ def test_slab_handle_rejects_what_it_cannot_do():
         s.next_step(DT)                                     # not attached yet
     with pytest.raises(tfs.TfsError):
         s.resize(128, 64)
+    with pytest.raises(tfs.TfsError):
+        s.set_options(kernel=tfs.KERNEL_DIAGONAL)           # would index slab-local buffers with global columns
+    with pytest.raises(tfs.TfsError):
+        s.set_options(iterations=0)
+    with pytest.raises(tfs.TfsError):
+        tfs.FluidSim(256, 64, rank=0, world=2, kernel=tfs.KERNEL_DIAGONAL)
     s.close()
