@@ -24,20 +24,25 @@ def run(tag, cfg, env=None):
     r = subprocess.run([sys.executable, "-c", CHILD, json.dumps(cfg)], env=e, capture_output=True, text=True, timeout=600)
     print(tag, cfg, env or {}, "->", r.stdout.strip() or r.stderr.strip()[-400:], flush=True)
 
-c3 = [4096, 4096, 100, 9.8, 0, 10, "none"]
-c5 = [32768, 32768, 200, 0.0, 0, 3, "random"]
-run("c3 exact default", c3)
-run("c3 exact (5,4)", c3, {"TFS_SYS_KG": "5", "TFS_SYS_NW": "4"})
-run("c3 exact (6,4)", c3, {"TFS_SYS_KG": "6", "TFS_SYS_NW": "4"})
-run("c3 exact (4,3)", c3, {"TFS_SYS_KG": "4", "TFS_SYS_NW": "3"})
-run("c3 rb fused", [4096, 4096, 100, 9.8, 1, 10, "none"])
-run("c3 rb fused lx256", [4096, 4096, 100, 9.8, 1, 10, "none"], {"TFS_RB_CHUNK": "256"})
-run("c3 rb fused lx64", [4096, 4096, 100, 9.8, 1, 10, "none"], {"TFS_RB_CHUNK": "64"})
-run("c3 rb two-launch", [4096, 4096, 100, 9.8, 1, 3, "none"], {"TFS_RB_VARIANT": "1"})
-for v in range(5):
-    run("c3 advect variant %d" % v, [4096, 4096, 4, 9.8, 0, 20, "none"], {"TFS_ADV_VARIANT": str(v)})
-run("c4 exact", [16384, 16384, 50, 0.0, 0, 3, "lattice"])
-run("c4 rb", [16384, 16384, 50, 0.0, 1, 3, "lattice"])
-run("c5 exact default", c5)
-run("c5 exact (5,4)", c5, {"TFS_SYS_KG": "5", "TFS_SYS_NW": "4"})
-run("c5 rb", [32768, 32768, 200, 0.0, 1, 3, "random"])
+def main():
+    c3 = [4096, 4096, 100, 9.8, 0, 10, "none"]
+    c5 = [32768, 32768, 200, 0.0, 0, 3, "random"]
+    run("c3 exact default", c3)
+    run("c3 exact (5,4)", c3, {"TFS_SYS_KG": "5", "TFS_SYS_NW": "4"})
+    run("c3 exact (6,4)", c3, {"TFS_SYS_KG": "6", "TFS_SYS_NW": "4"})
+    run("c3 exact (4,3)", c3, {"TFS_SYS_KG": "4", "TFS_SYS_NW": "3"})
+    run("c3 rb fused", [4096, 4096, 100, 9.8, 1, 10, "none"])
+    run("c3 rb fused lx256", [4096, 4096, 100, 9.8, 1, 10, "none"], {"TFS_RB_CHUNK": "256"})
+    run("c3 rb fused lx64", [4096, 4096, 100, 9.8, 1, 10, "none"], {"TFS_RB_CHUNK": "64"})
+    run("c3 rb two-launch", [4096, 4096, 100, 9.8, 1, 3, "none"], {"TFS_RB_VARIANT": "1"})
+    for v in range(5):
+        run("c3 advect variant %d" % v, [4096, 4096, 4, 9.8, 0, 20, "none"], {"TFS_ADV_VARIANT": str(v)})
+    run("c4 exact", [16384, 16384, 50, 0.0, 0, 3, "lattice"])
+    run("c4 rb", [16384, 16384, 50, 0.0, 1, 3, "lattice"])
+    run("c5 exact default", c5)
+    run("c5 exact (5,4)", c5, {"TFS_SYS_KG": "5", "TFS_SYS_NW": "4"})
+    run("c5 rb", [32768, 32768, 200, 0.0, 1, 3, "random"])
+
+
+if __name__ == "__main__":
+    main()
