@@ -240,6 +240,9 @@ def run_ours(args):
     if args.workload == "c5" and not args.no_extra:
         extra["config3_4096"] = side_workload(tfs, "c3", local_rank, peak, steps=10, warmup=3)
         extra["config4_16384"] = side_workload(tfs, "c4", local_rank, peak, steps=5, warmup=3)
+        # the same frame loop through include/fluid_sim.hpp, the C++ mirror of `impl FluidSim` (set_block brush,
+        # next_step, render_view): its next_step() copies nothing back, the frame's D2H is the visible window only
+        extra["e2e_cpp_mirror"] = {k: cpp_mirror_frames(WORKLOADS[k], frames) for k, frames in (("c3", 10), ("c5", 3))}
 
     cpu = cpu_baseline(args.workload, steps=2, warmup=1) if not args.no_cpu else None
 
@@ -256,6 +259,16 @@ def run_ours(args):
     }
     if rank == 0:
         print(json.dumps(out))
+
+
+def cpp_mirror_frames(w, frames, mode=0):
+    from terminal_fluid_sim_b200 import build as tfs_build
+    try:
+        r = subprocess.run([tfs_build.E2E, str(w["W"]), str(w["H"]), str(w["K"]), str(w["gravity"]), w["scene"], str(frames), str(mode)],
+                           capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # the headline numbers do not depend on this leg
+        return {"error": repr(e)}
 
 
 def side_workload(tfs, key, device, peak, steps, warmup, group=None):

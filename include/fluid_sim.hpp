@@ -3,6 +3,13 @@
 // include/tfs.h.  Same method names, argument meaning and error behaviour: where the reference
 // panics this throws.  (The reference's host language is Rust; the equivalent Rust wrapper is under
 // rust/ -- this header exists because only C/C++ can be compiled in the build image.)
+//
+// The state lives on the device.  next_step() only enqueues the step: nothing is copied back.  The
+// whole-grid `&Vec` accessors of the reference (get_pressure_grid / get_smoke_grid, simulator.rs:316-328)
+// are served from host mirrors that are fetched LAZILY, on the first accessor call after a change; a
+// renderer that wants only the visible window uses render_view() (8 bytes per terminal cell) and never
+// triggers the whole-grid copy.  `cargo bench`'s loop (benches/benchmarks/sim_bench.rs:9) therefore does no
+// device-to-host traffic at all.
 #pragma once
 #include <chrono>
 #include <cstdint>
@@ -33,7 +40,7 @@ public:
     FluidSim &operator=(FluidSim &&o) noexcept {
         std::swap(h_, o.h_); std::swap(width_, o.width_); std::swap(height_, o.height_);
         pressure_.swap(o.pressure_); smoke_.swap(o.smoke_); block_.swap(o.block_);
-        std::swap(last_, o.last_);
+        std::swap(last_, o.last_); std::swap(p_stale_, o.p_stale_); std::swap(s_stale_, o.s_stale_);
         return *this;
     }
     ~FluidSim() { if (h_) tfs_destroy(h_); }
@@ -41,7 +48,8 @@ public:
     void resize(size_t width, size_t height) {  // :43
         check(tfs_resize(h_, width, height));
         width_ = width; height_ = height;
-        refresh_all();
+        refresh_blocks();  // resize_block_grid scrambles the mask (simulator.rs:121-135): the device is authoritative
+        p_stale_ = s_stale_ = true;
         last_ = clock::now();
     }
     void restart_sim() { resize(width_, height_); }  // :55
@@ -52,21 +60,21 @@ public:
         next_step(dt);
     }
     void next_step(float dt) {  // deterministic variant used by tests and benches
-        check(tfs_step(h_, dt));
-        refresh_fields();
+        check(tfs_step(h_, dt));  // asynchronous on the device; no copy back
+        p_stale_ = s_stale_ = true;
         last_ = clock::now();
     }
     void set_config(const SimConfig &c) {  // :67
         tfs_config cc{c.gravity, c.wind_speed, c.smoke_size, c.density};
         check(tfs_set_config(h_, &cc));
-        refresh_fields();
+        s_stale_ = true;  // only the smoke pipe (and u) change (simulator.rs:67-71)
     }
     size_t calculate_index(size_t x, size_t y) const { return calculate_index_with_height(height_, x, y); }  // :301
     static size_t calculate_index_with_height(size_t height, size_t x, size_t y) { return x * height + y; }   // :306
     std::pair<size_t, size_t> get_size() const { return {width_, height_}; }                                  // :311
-    const std::vector<float> &get_pressure_grid() const { return pressure_; }                                  // :316
+    const std::vector<float> &get_pressure_grid() const { fetch(TFS_FIELD_P, pressure_, p_stale_); return pressure_; }  // :316
     const std::vector<uint8_t> &get_block_grid() const { return block_; }                                      // :321
-    const std::vector<float> &get_smoke_grid() const { return smoke_; }                                        // :326
+    const std::vector<float> &get_smoke_grid() const { fetch(TFS_FIELD_S, smoke_, s_stale_); return smoke_; }  // :326
     void set_block(size_t x, size_t y) { edit_block(x, y, 1); }                                                // :331
     void unset_block(size_t x, size_t y) { edit_block(x, y, 0); }                                              // :337
 
@@ -85,7 +93,14 @@ private:
         tfs_config cc{c.gravity, c.wind_speed, c.smoke_size, c.density};
         check(tfs_create(w, h, &cc, opt, &h_));
         width_ = w; height_ = h;
-        refresh_all();
+        try {
+            refresh_blocks();
+        } catch (...) {
+            tfs_destroy(h_);
+            h_ = nullptr;
+            throw;
+        }
+        p_stale_ = s_stale_ = true;
         last_ = clock::now();
     }
     void edit_block(size_t x, size_t y, int value) {
@@ -96,14 +111,14 @@ private:
         check(tfs_set_block(h_, x, y, value));
         block_[idx] = (uint8_t)value;
     }
-    void refresh_fields() {
-        const size_t n = width_ * height_;
-        pressure_.resize(n); smoke_.resize(n);
-        check(tfs_read_field(h_, TFS_FIELD_P, pressure_.data(), n));
-        check(tfs_read_field(h_, TFS_FIELD_S, smoke_.data(), n));
+    // whole-grid D2H of one field, only when an accessor asks for it after the device copy changed
+    void fetch(int field, std::vector<float> &dst, bool &stale) const {
+        if (!stale) return;
+        dst.resize(width_ * height_);
+        check(tfs_read_field(h_, field, dst.data(), dst.size()));
+        stale = false;
     }
-    void refresh_all() {
-        refresh_fields();
+    void refresh_blocks() {
         block_.resize(width_ * height_);
         check(tfs_read_field(h_, TFS_FIELD_M, block_.data(), block_.size()));
     }
@@ -112,8 +127,9 @@ private:
     }
     tfs_sim *h_ = nullptr;
     size_t width_ = 0, height_ = 0;
-    std::vector<float> pressure_, smoke_;
-    std::vector<uint8_t> block_;
+    mutable std::vector<float> pressure_, smoke_;  // host mirrors, valid while !p_stale_ / !s_stale_
+    mutable bool p_stale_ = true, s_stale_ = true;
+    std::vector<uint8_t> block_;                   // host-authoritative between resizes (edits go both ways)
     clock::time_point last_{};
 };
 

@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtfs_cuda.so")
+E2E = os.path.join(HERE, "host", "e2e_mirror")          # frame loop through include/fluid_sim.hpp (C++ host mirror)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,11 +34,12 @@ def _nvcc() -> str:
 
 def sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
-           [os.path.join(os.path.dirname(HERE), "include", "tfs.h")]
+           [os.path.join(os.path.dirname(HERE), "include", "tfs.h"), os.path.join(os.path.dirname(HERE), "include", "fluid_sim.hpp"),
+            os.path.join(HERE, "host", "e2e_mirror.cpp")]
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(E2E):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in sources())
@@ -63,7 +65,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libtfs_cuda.so")
     if verbose:
         print(log)
+    build_host_mirror(host or "g++")
     return LIB
+
+
+def build_host_mirror(cxx: str = "g++") -> str:
+    """the C++ host-side mirror's frame loop (host/e2e_mirror.cpp): plain g++, links the C ABI only"""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    cmd = [cxx, "-O2", "-std=c++17", "-I", inc, os.path.join(HERE, "host", "e2e_mirror.cpp"), "-o", E2E, LIB,
+           "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building host/e2e_mirror")
+    return E2E
 
 
 if __name__ == "__main__":

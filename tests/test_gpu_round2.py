@@ -253,3 +253,27 @@ def test_two_virtual_slabs_on_one_device_match_oracle(mode):
             assert bits_equal(a, b), f"mode {mode} step {st} {n}: " + first_mismatch(a, b, H)
     assert np.array_equal(grp.checksum(), tfs.checksum_of_fields(o.u, o.v, o.p, o.s))
     grp.close()
+
+
+# ---- the C++ host mirror (include/fluid_sim.hpp) ------------------------------------------------------------------
+def test_cpp_mirror_frame_loop_computes_the_same_bits_as_the_ctypes_mirror():
+    """host/e2e_mirror drives brush edits, next_step and render_view through include/fluid_sim.hpp; the ctypes mirror
+    repeats the same calls.  Same state checksum, and the C++ next_step() does no whole-grid read-back (by construction:
+    the mirrors are fetched lazily by the get_*_grid accessors only)."""
+    import json
+    import subprocess
+    from terminal_fluid_sim_b200 import build as tfs_build
+    W, H, K, frames = 512, 256, 20, 4
+    out = subprocess.run([tfs_build.E2E, str(W), str(H), str(K), "1.5", "disc", str(frames), "0"], capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout)
+    g = tfs.FluidSim(W, H, tfs.SimConfig(gravity=1.5), iterations=K)
+    g.scene_disc(256, 512, 128)
+    for i in range(3 + frames):
+        x = 8 + i % 8
+        for y in range(H // 2 - 4, H // 2 + 4):
+            (g.unset_block if i & 1 else g.set_block)(x, y)
+        g.next_step(DT)
+    assert got["checksum"] == ["%016x" % int(v) for v in g.checksum()]
+    assert got["d2h_bytes_per_frame"] == 512 * 128 * 8 + 8
