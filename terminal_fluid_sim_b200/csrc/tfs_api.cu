@@ -858,6 +858,11 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
         CU(cudaEventCreateWithFlags(&s->oob_ev, cudaEventDisableTiming));
         return TFS_OK;
     }());
+    if (s->slab()) CREATE_TRY([&]() -> int {  // nothing may be allocated inside a slab step (see systolic4_reserve)
+        CU(tfs::systolic4_reserve(s->sys4, (size_t)s->lay.max_passes * (size_t)(s->lay.cstride - 2)));
+        CU(cudaMalloc((void **)&s->d_sum, 8 * sizeof(unsigned long long)));
+        return TFS_OK;
+    }());
     CREATE_TRY(reset_fields(s));
     // make_block_grid (simulator.rs:113-119): the left border column is solid
     tfs::k_fill_range_u8<<<blocks_for((long long)std::min(height, width * height), 256), 256, 0, s->stream>>>(

@@ -106,6 +106,7 @@ struct Tunables {
     char advect = 0;              // TFS_ADVECT = vec4 / scalar: generic advection kernels
     int adv_variant = 0;          // TFS_ADV_VARIANT = n: experimental advection variants
     int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
+    int rb_pf = 0;                // TFS_RB_PF = n: L2 prefetch distance (columns) of the fused red-black kernel
     int rb_chunk = 0;             // TFS_RB_CHUNK = n: columns per chunk of the fused red-black kernel (0 = default)
     const char *task_trace_prefix = nullptr;
 };
@@ -124,6 +125,7 @@ inline const Tunables &tunables() {
         x.adv_variant = geti("TFS_ADV_VARIANT", 0);
         x.rb_variant = geti("TFS_RB_VARIANT", 0);
         x.rb_chunk = geti("TFS_RB_CHUNK", 0);
+        x.rb_pf = geti("TFS_RB_PF", 0);
         x.task_trace_prefix = getenv("TFS_TASK_TRACE_PREFIX");
         return x;
     }();

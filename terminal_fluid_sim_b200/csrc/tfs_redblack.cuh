@@ -39,6 +39,7 @@ struct RbParams {
     int n_strips;        // strips of V = 64 - 2*NS rows
     int chunk0, lx;      // first column chunk (global index), chunk length (multiple of NS)
     int ns_act;          // active stages of this pass (2 * iterations fused in it)
+    int pf;              // L2 prefetch distance in columns (0 = none)
     int apply_gravity;   // first pass: v += gdt on updatable cells while loading (simulator.rs:137-149)
     float omega, pc, gdt;
 };
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     // use, which leaves far too few bytes in flight per SM to cover the DRAM latency (measured: 45 % of the HBM rate).
     // One predicated prefetch.global.L2 per step asks for the warp's segments of column x + PF: lanes 0-2 the (up to)
     // three 128-byte lines of u, 3-5 of v, 6-8 of p, lane 9 the flags line.
-    constexpr int PF = 6;
+    const int PF = P.pf;  // 0 = off
     const int seg_row = strip * V - NS;                    // first row of the warp's segment (may lie outside the grid)
     auto prefetch_col = [&](int i) {
         const int li = i - xs0;
@@ -107,15 +108,17 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         }
     };
     int x = gx0 - NS;          // newest column held (the "pending" one): stage s works on column x-1-s
+    if (PF > 0) {
 #pragma unroll 1
-    for (int d = 0; d <= PF; ++d) prefetch_col(x + d);
+        for (int d = 0; d <= PF; ++d) prefetch_col(x + d);
+    }
     Col pend = load_col(x);    // its u is the right face of column x-1; v, p, flags wait for the next step
     const int n_it = (P.lx + 2 * NS) / NS;
     for (int it = 0; it < n_it; ++it) {
 #pragma unroll
         for (int m = 0; m < NS; ++m, ++x) {  // x % NS == m, x % 2 == m % 2
             const Col nxt = load_col(x + 1);  // consumed at the end of this step
-            prefetch_col(x + 1 + PF);
+            if (PF > 0) prefetch_col(x + 1 + PF);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 if (s < ns_act) {
@@ -191,6 +194,7 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.ns_act = 2 * k_act;
     P.apply_gravity = (t == 0 && a.apply_gravity) ? 1 : 0;
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
+    P.pf = tunables().rb_pf;
     dim3 grid((unsigned)((P.n_strips + 3) / 4), (unsigned)n_chunks);
     if (t == 0) k_project_rb<KB, true><<<grid, 128, 0, stream>>>(P);
     else k_project_rb<KB, false><<<grid, 128, 0, stream>>>(P);

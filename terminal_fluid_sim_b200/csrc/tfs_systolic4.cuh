@@ -646,6 +646,21 @@ struct Systolic4Workspace {
     int last_kg = 0, last_nw = 0, last_passes = 0;  // shape of the last launch (tfs_get_last_projection)
 };
 
+// Allocate the task list up front (x-slab handles: tfs_create).  cudaMalloc waits for the device to go idle, which
+// inside a step would deadlock two slab handles that share ONE device (the other rank's kernels spin on flags this
+// rank has not raised yet).
+inline cudaError_t systolic4_reserve(Systolic4Workspace &ws4, size_t n_tasks) {
+    if (ws4.n_tasks_cap >= n_tasks) return cudaSuccess;
+    if (ws4.d_tasks) cudaFree(ws4.d_tasks);
+    if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
+    ws4.d_tasks = nullptr; ws4.h_tasks = nullptr; ws4.n_tasks_cap = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&ws4.d_tasks, n_tasks * sizeof(int2))) != cudaSuccess) return e;
+    if ((e = cudaMallocHost((void **)&ws4.h_tasks, n_tasks * sizeof(int2))) != cudaSuccess) return e;
+    ws4.n_tasks_cap = n_tasks;
+    return cudaSuccess;
+}
+
 template <int KG, int NW, int G, int RB>
 struct Sys4Launch {
     static constexpr int KB = KG * NW;
@@ -746,14 +761,7 @@ struct Sys4Launch {
         const long long n_tasks = (long long)P.n_passes * SL.nb_local;
         if (ws4.key_W != a.W || ws4.key_H != a.H || ws4.key_passes != P.n_passes || ws4.key_bands != P.n_bands ||
             ws4.key_b0 != SL.b0 || ws4.key_nbl != SL.nb_local || ws4.key_kb != KB) {
-            if (ws4.n_tasks_cap < (size_t)n_tasks) {
-                if (ws4.d_tasks) cudaFree(ws4.d_tasks);
-                if (ws4.h_tasks) cudaFreeHost(ws4.h_tasks);
-                ws4.d_tasks = nullptr; ws4.h_tasks = nullptr; ws4.n_tasks_cap = 0;
-                if ((e = cudaMalloc((void **)&ws4.d_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
-                if ((e = cudaMallocHost((void **)&ws4.h_tasks, (size_t)n_tasks * sizeof(int2))) != cudaSuccess) { *msg = "task list allocation"; return e; }
-                ws4.n_tasks_cap = (size_t)n_tasks;
-            }
+            if ((e = systolic4_reserve(ws4, (size_t)n_tasks)) != cudaSuccess) { *msg = "task list allocation"; return e; }
             // Issue order.  "diag": key = start time (a band trails its left neighbour by ~lag_b steps, the
             // previous pass by ~lag_t): all passes advance together, good when every task is resident.
             // "lex": pass-major.  With more tasks than CTA slots the diagonal order makes the band chain of
