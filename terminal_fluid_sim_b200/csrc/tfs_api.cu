@@ -299,6 +299,27 @@ int check_options(const tfs_options *o) {
     return TFS_OK;
 }
 
+// CUDA loads kernels lazily, and loading one may wait for the device to go idle.  An x-slab step enqueues kernels
+// that spin on flags raised by ANOTHER handle's kernels; when one host thread drives several handles (SlabGroup,
+// or two handles on one device) a first-time launch behind such a spinning kernel would then never return.  So a
+// slab handle loads every kernel of the step path when it is created.  (Measured: two handles on one B200 dead-
+// locked in their first step without this, and ran with CUDA_MODULE_LOADING=EAGER.)
+void preload_step_kernels() {
+    cudaFuncAttributes fa;
+    const void *fns[] = {(const void *)tfs::k_cell_flags, (const void *)tfs::k_flag_wait2, (const void *)tfs::k_flag_set,
+                         (const void *)tfs::k_copy_f4, (const void *)tfs::k_advect32<8, true, false>,
+                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true>,
+                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, false>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, false>,
+                         (const void *)tfs::k_fill_f32, (const void *)tfs::k_fill_range_f32, (const void *)tfs::k_fill_range_u8,
+                         (const void *)tfs::k_checksum, (const void *)tfs::k_minmax_partial, (const void *)tfs::k_minmax_final,
+                         (const void *)tfs::k_div_partial, (const void *)tfs::k_pack_view<float>, (const void *)tfs::k_pack_view<uint8_t>,
+                         (const void *)tfs::k_render_view, (const void *)tfs::k_scene_disc, (const void *)tfs::k_scene_lattice,
+                         (const void *)tfs::k_scene_random, (const void *)tfs::k_fill_random_velocity};
+    for (const void *f : fns) cudaFuncGetAttributes(&fa, f);
+    tfs::systolic4_preload();
+    cudaGetLastError();
+}
+
 // what an x-slab handle can run (tfs_create and tfs_set_options)
 int check_slab_options(const tfs_options *o) {
     NEED(o->kernel != TFS_KERNEL_DIAGONAL, TFS_ERR_INVALID_ARG,
@@ -858,6 +879,7 @@ int tfs_create(size_t width, size_t height, const tfs_config *cfg, const tfs_opt
         CU(cudaEventCreateWithFlags(&s->oob_ev, cudaEventDisableTiming));
         return TFS_OK;
     }());
+    if (s->slab()) preload_step_kernels();
     if (s->slab()) CREATE_TRY([&]() -> int {  // nothing may be allocated inside a slab step (see systolic4_reserve)
         CU(tfs::systolic4_reserve(s->sys4, (size_t)s->lay.max_passes * (size_t)(s->lay.cstride - 2)));
         CU(cudaMalloc((void **)&s->d_sum, 8 * sizeof(unsigned long long)));

@@ -44,10 +44,12 @@ struct RbParams {
     float omega, pc, gdt;
 };
 
-template <int KB, bool FIRST>
+// FULL: all NS stages of the pass are active (every pass but a shorter last one), so no per-stage test is issued.
+template <int KB, bool FIRST, bool FULL>
 __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
     constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
+    constexpr unsigned ALL_PLAIN = (1u << NS) - 1u;
     static_assert(V >= 8, "too many fused iterations for a 64-row strip");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * 4 + warp;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     const bool store_lane = row_ok && lane >= KB && lane < 32 - KB;
     const int gx0 = (P.chunk0 + (int)blockIdx.y) * P.lx;  // first column this chunk finalises
     const int vx0 = max(gx0, P.c_lo), vx1 = min(gx0 + P.lx, P.c_hi);
-    const int ns_act = P.ns_act;
+    const int ns_act = FULL ? NS : P.ns_act;
     const float omega = P.omega, pc = P.pc;
 
     // register window: slot c holds column i with i % NS == c (rows A = lower, B = upper)
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
 #pragma unroll
     for (int c = 0; c < NS; ++c) { uA[c] = uB[c] = vA[c] = vB[c] = pA[c] = pB[c] = 0.0f; fl[c] = 0u; }
 
+    // this lane's element offset inside a stored column, and the running offset of the column being loaded
+    const size_t row_off = (size_t)(row_ok ? rA : 0);
     struct Col { float2 u, v, p; unsigned f; };
     auto load_col = [&](int i) -> Col {
         Col r;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         r.f = 0u;
         const int li = i - xs0;
         if (row_ok && (unsigned)li < (unsigned)ncols) {  // stored columns lie inside the grid
-            const size_t o = (size_t)li * (size_t)H + (size_t)rA;
+            const size_t o = (size_t)li * (size_t)H + row_off;
             r.u = __ldg(reinterpret_cast<const float2 *>(P.in_u + o));
             r.v = __ldg(reinterpret_cast<const float2 *>(P.in_v + o));
             if (!FIRST) r.p = __ldg(reinterpret_cast<const float2 *>(P.in_p + o));
@@ -88,25 +92,28 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         return r;
     };
 
-    // Deep prefetch without registers: the loads above are issued only one march step (~200 issue slots) before their
-    // use, which leaves far too few bytes in flight per SM to cover the DRAM latency (measured: 45 % of the HBM rate).
-    // One predicated prefetch.global.L2 per step asks for the warp's segments of column x + PF: lanes 0-2 the (up to)
-    // three 128-byte lines of u, 3-5 of v, 6-8 of p, lane 9 the flags line.
-    const int PF = P.pf;  // 0 = off
-    const int seg_row = strip * V - NS;                    // first row of the warp's segment (may lie outside the grid)
-    auto prefetch_col = [&](int i) {
-        const int li = i - xs0;
-        if (lane < 10 && (unsigned)li < (unsigned)ncols) {
-            const int f = lane / 3, part = lane - 3 * f;  // f: 0 u, 1 v, 2 p, 3 flags
-            if (!(FIRST && f == 2)) {
-                const int r0 = min(max(seg_row + (f == 3 ? 0 : part * 32), 0), H - 1);
-                const size_t o = (size_t)li * (size_t)H + (size_t)r0;
-                const void *ptr = f == 0 ? (const void *)(P.in_u + o) : f == 1 ? (const void *)(P.in_v + o)
-                                : f == 2 ? (const void *)(P.in_p + o) : (const void *)(P.flags + o);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-            }
+    // Deep prefetch without registers: the loads above are issued one march step (~200 issue slots) before their use,
+    // which leaves too few bytes in flight per SM to cover the DRAM latency (ncu: long_scoreboard 3.3 cycles per issued
+    // instruction).  Lanes 0-9 each own one 128-byte line of the warp's segment (0-2: u, 3-5: v, 6-8: p, 9: flags) and
+    // ask the L2 for it P.pf columns ahead: one pointer increment and one prefetch.global.L2 per step.
+    const int PF = P.pf;
+    const char *pf_ptr = nullptr;
+    size_t pf_stride = 0;
+    if (PF > 0 && lane < 10) {
+        const int f = lane / 3, part = lane - 3 * f;
+        if (!(FIRST && f == 2)) {
+            const int r0 = min(max(strip * V - NS + (f == 3 ? 0 : part * 32), 0), H - 1);
+            const char *base = f == 0 ? (const char *)P.in_u : f == 1 ? (const char *)P.in_v : f == 2 ? (const char *)P.in_p : (const char *)P.flags;
+            const size_t esz = f == 3 ? 1 : 4;
+            pf_stride = (size_t)H * esz;
+            pf_ptr = base + (size_t)r0 * esz + (size_t)(gx0 - NS - xs0) * pf_stride;  // column gx0 - NS (may lie outside: checked below)
         }
+    }
+    auto prefetch_col = [&](int i) {  // pf_ptr points at column i
+        if (pf_ptr && (unsigned)(i - xs0) < (unsigned)ncols) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr));
+        pf_ptr += pf_stride;          // (a null pointer stays harmless: stride 0)
     };
+
     int x = gx0 - NS;          // newest column held (the "pending" one): stage s works on column x-1-s
     if (PF > 0) {
 #pragma unroll 1
@@ -119,27 +126,54 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         for (int m = 0; m < NS; ++m, ++x) {  // x % NS == m, x % 2 == m % 2
             const Col nxt = load_col(x + 1);  // consumed at the end of this step
             if (PF > 0) prefetch_col(x + 1 + PF);
+            // colour of half-sweep s = s & 1; the lower cell (even row) of column i = x-1-s is active when
+            // (i & 1) == (s & 1), i.e. when m is odd -- a compile-time fact of the unrolled step
+            constexpr int dummy = 0; (void)dummy;
+            const bool lower = (m & 1) != 0;
+            if (FULL && plain == ALL_PLAIN) {
+                // every cell the NS stages touch is plain interior fluid: straight-line code, no flag work at all
+                if (lower) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                if (s < ns_act) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int c = (m - 1 - s + 2 * NS) % NS;  // slot of column x-1-s
-                    const int cn = (c + 1) % NS;              // slot of column x-s (s == 0: the pending column)
-                    // colour of the half-sweep = s & 1; the lower cell (even row) of column i is active when
-                    // (i & 1) == (s & 1), i.e. when m is odd -- a compile-time fact
-                    const bool lower = (m & 1) != 0;
-                    const bool is_plain = (plain >> c) & 1u;
-                    if (lower) {
+                    for (int s = 0; s < NS; ++s) {
+                        const int c = (m - 1 - s + 2 * NS) % NS, cn = (c + 1) % NS;
                         float &uR = (s == 0) ? pend.u.x : uA[cn];
-                        if (is_plain) cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
-                        else cell_update4<2>(fl[c] & 15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
-                    } else {
+                        cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                    }
+                } else {
+                    float vT[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) vT[s] = __shfl_down_sync(0xffffffffu, vA[(m - 1 - s + 2 * NS) % NS], 1);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const int c = (m - 1 - s + 2 * NS) % NS, cn = (c + 1) % NS;
                         float &uR = (s == 0) ? pend.u.y : uB[cn];
-                        float vT = __shfl_down_sync(0xffffffffu, vA[c], 1);  // lane 31: its own value, inside the overlap
-                        if (is_plain) cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
-                        else cell_update4<2>((fl[c] >> 8) & 15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
-                        vT = __shfl_up_sync(0xffffffffu, vT, 1);
-                        if (lane > 0) vA[c] = vT;
+                        cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT[s], pB[c]);
+                    }
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const float t = __shfl_up_sync(0xffffffffu, vT[s], 1);
+                        if (lane > 0) vA[(m - 1 - s + 2 * NS) % NS] = t;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    if (FULL || s < ns_act) {
+                        const int c = (m - 1 - s + 2 * NS) % NS;  // slot of column x-1-s
+                        const int cn = (c + 1) % NS;              // slot of column x-s (s == 0: the pending column)
+                        const bool is_plain = (plain >> c) & 1u;
+                        if (lower) {
+                            float &uR = (s == 0) ? pend.u.x : uA[cn];
+                            if (is_plain) cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                            else cell_update4<2>(fl[c] & 15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                        } else {
+                            float &uR = (s == 0) ? pend.u.y : uB[cn];
+                            float vT = __shfl_down_sync(0xffffffffu, vA[c], 1);  // lane 31: its own value, inside the overlap
+                            if (is_plain) cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
+                            else cell_update4<2>((fl[c] >> 8) & 15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
+                            vT = __shfl_up_sync(0xffffffffu, vT, 1);
+                            if (lane > 0) vA[c] = vT;
+                        }
                     }
                 }
             }
@@ -147,7 +181,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
             {
                 const int i = x - NS;
                 if (store_lane && i >= vx0 && i < vx1) {
-                    const size_t o = (size_t)(i - xs0) * (size_t)H + (size_t)rA;
+                    const size_t o = (size_t)(i - xs0) * (size_t)H + row_off;
                     *reinterpret_cast<float2 *>(P.out_u + o) = make_float2(uA[m], uB[m]);
                     *reinterpret_cast<float2 *>(P.out_v + o) = make_float2(vA[m], vB[m]);
                     *reinterpret_cast<float2 *>(P.out_p + o) = make_float2(pA[m], pB[m]);
@@ -196,8 +230,9 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
     P.pf = tunables().rb_pf;
     dim3 grid((unsigned)((P.n_strips + 3) / 4), (unsigned)n_chunks);
-    if (t == 0) k_project_rb<KB, true><<<grid, 128, 0, stream>>>(P);
-    else k_project_rb<KB, false><<<grid, 128, 0, stream>>>(P);
+    const bool full = k_act == KB;
+    if (t == 0) { if (full) k_project_rb<KB, true, true><<<grid, 128, 0, stream>>>(P); else k_project_rb<KB, true, false><<<grid, 128, 0, stream>>>(P); }
+    else { if (full) k_project_rb<KB, false, true><<<grid, 128, 0, stream>>>(P); else k_project_rb<KB, false, false><<<grid, 128, 0, stream>>>(P); }
     return cudaGetLastError();
 }
 

@@ -891,6 +891,19 @@ inline void systolic4_release(Systolic4Workspace &ws4) {
 // count: every shape systolic_pick can return for v4_only has a case below.
 inline bool systolic4_usable(const SystolicArgs &a) { return (a.H % 4) == 0 && !tunables().sys_v3; }
 
+// Force the lazy loader to load every block-ring instantiation now (see preload_step_kernels in tfs_api.cu).
+inline void systolic4_preload() {
+    cudaFuncAttributes fa;
+#define TFS_SYS4_PRELOAD(KG_, NW_) cudaFuncGetAttributes(&fa, k_project_systolic4<KG_, NW_, 8, 16>);
+    TFS_SYS4_PRELOAD(4, 4) TFS_SYS4_PRELOAD(5, 4) TFS_SYS4_PRELOAD(6, 4) TFS_SYS4_PRELOAD(4, 8) TFS_SYS4_PRELOAD(4, 3)
+    TFS_SYS4_PRELOAD(2, 5) TFS_SYS4_PRELOAD(4, 2) TFS_SYS4_PRELOAD(2, 8) TFS_SYS4_PRELOAD(2, 4) TFS_SYS4_PRELOAD(2, 2)
+    TFS_SYS4_PRELOAD(5, 2) TFS_SYS4_PRELOAD(1, 8) TFS_SYS4_PRELOAD(8, 2) TFS_SYS4_PRELOAD(8, 4) TFS_SYS4_PRELOAD(8, 1)
+#undef TFS_SYS4_PRELOAD
+    cudaFuncGetAttributes(&fa, k_project_systolic4<4, 4, 4, 32>);
+    cudaFuncGetAttributes(&fa, k_project_systolic4<4, 4, 8, 32>);
+    cudaGetLastError();
+}
+
 inline cudaError_t systolic_project_auto(const SystolicArgs &a, const Sys4External *ext, SystolicWorkspace &ws,
                                          Systolic4Workspace &ws4, uint64_t *launched, const char **msg) {
     ws4.last_kg = ws4.last_nw = ws4.last_passes = 0;
