@@ -268,6 +268,11 @@ TFS_DEVINL float magic_float(float y, float one) { return __fmaf_rn(y, one, -TFS
 
 // SLAB: `f` is a global-column base (storage pointer - xs0*H); columns outside the stored range
 // [cs0, cs1] are clamped for memory safety and reported through *oob (halo too small for this dt).
+// field load: x-slab kernels bypass L1 (ld.global.cg).  Their halo columns are rewritten between launches by another
+// stream (the neighbour's push); with two slabs on ONE device an L1 line from an earlier launch could be stale.
+template <bool SLAB>
+TFS_DEVINL float ldf(const float *p) { return SLAB ? __ldcg(p) : __ldg(p); }
+
 template <int FT, bool SLAB = false>
 TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, int W, int H, float Wf, float Hf,
                                 float one, unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
@@ -295,8 +300,8 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
         }
     }
     const unsigned i00 = xls * (unsigned)H + yb, i10 = i00 + dxo;
-    const float f00 = __ldg(f + i00), f10 = __ldg(f + i10);
-    const float f11 = __ldg(f + i10 + dyo), f01 = __ldg(f + i00 + dyo);
+    const float f00 = ldf<SLAB>(f + i00), f10 = ldf<SLAB>(f + i10);
+    const float f11 = ldf<SLAB>(f + i10 + dyo), f01 = ldf<SLAB>(f + i00 + dyo);
     return fadd_f(fadd_f(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11), one),
                   fmul(fmul(sx, ty), f01), one);   // :294-297
 }
@@ -365,17 +370,17 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
     const int jm = j > 0 ? j - 1 : 0, jp = j < H - 1 ? j + 1 : j;   // clamped only for memory safety (border rows never use them)
     unsigned idx = (unsigned)i0 * (unsigned)H + (unsigned)j;
     // values of column i (own) and column i-1 (left)
-    float uC = u[idx], vC = v[idx], uB = u[idx - j + jm], vT = v[idx - j + jp];
+    float uC = ldf<SLAB>(u + idx), vC = ldf<SLAB>(v + idx), uB = ldf<SLAB>(u + (idx - j + jm)), vT = ldf<SLAB>(v + (idx - j + jp));
     float vL = 0.0f, vLT = 0.0f;
-    if (i0 > 0) { vL = v[idx - H]; vLT = v[idx - H - j + jp]; }
+    if (i0 > 0) { vL = ldf<SLAB>(v + (idx - H)); vLT = ldf<SLAB>(v + (idx - H - j + jp)); }
 #pragma unroll
     for (int c = 0; c < CPB; ++c) {
         const int i = i0 + c;
         if (i >= W || i >= c_end) break;
         // column i+1 (right); clamped at the right border for memory safety only
         const unsigned idr = (i + 1 < W) ? idx + (unsigned)H : idx;
-        const float uR = u[idr], uRB = u[idr - j + jm], vR = v[idr], vRT = v[idr - j + jp];
-        const float sC = s[idx];
+        const float uR = ldf<SLAB>(u + idr), uRB = ldf<SLAB>(u + (idr - j + jm)), vR = ldf<SLAB>(v + idr), vRT = ldf<SLAB>(v + (idr - j + jp));
+        const float sC = ldf<SLAB>(s + idx);
         const unsigned f = flags[idx];
         float un = uC, vn = vC, sn = sC;
         const bool live = (f & TFS_F_LIVE) != 0u;

@@ -40,6 +40,7 @@ struct RbParams {
     int chunk0, lx;      // first column chunk (global index), chunk length (multiple of NS)
     int ns_act;          // active stages of this pass (2 * iterations fused in it)
     int pf;              // L2 prefetch distance in columns (0 = none)
+    int fast;            // 1: straight-line step when the whole window is plain fluid
     int apply_gravity;   // first pass: v += gdt on updatable cells while loading (simulator.rs:137-149)
     float omega, pc, gdt;
 };
@@ -80,9 +81,11 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         const int li = i - xs0;
         if (row_ok && (unsigned)li < (unsigned)ncols) {  // stored columns lie inside the grid
             const size_t o = (size_t)li * (size_t)H + row_off;
-            r.u = __ldg(reinterpret_cast<const float2 *>(P.in_u + o));
-            r.v = __ldg(reinterpret_cast<const float2 *>(P.in_v + o));
-            if (!FIRST) r.p = __ldg(reinterpret_cast<const float2 *>(P.in_p + o));
+            // ld.global.cg: the halo columns of a slab are rewritten between launches by ANOTHER stream (the neighbour's
+            // push); a line kept in L1 from an earlier launch would be stale when two slabs share one device
+            r.u = __ldcg(reinterpret_cast<const float2 *>(P.in_u + o));
+            r.v = __ldcg(reinterpret_cast<const float2 *>(P.in_v + o));
+            if (!FIRST) r.p = __ldcg(reinterpret_cast<const float2 *>(P.in_p + o));
             r.f = __ldg(reinterpret_cast<const unsigned short *>(P.flags + o));
             if (FIRST && P.apply_gravity) {
                 if (r.f & TFS_F_LIVE) r.v.x = fadd(r.v.x, P.gdt);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
             // (i & 1) == (s & 1), i.e. when m is odd -- a compile-time fact of the unrolled step
             constexpr int dummy = 0; (void)dummy;
             const bool lower = (m & 1) != 0;
-            if (FULL && plain == ALL_PLAIN) {
+            if (FULL && P.fast && plain == ALL_PLAIN) {
                 // every cell the NS stages touch is plain interior fluid: straight-line code, no flag work at all
                 if (lower) {
 #pragma unroll
@@ -229,6 +232,7 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.apply_gravity = (t == 0 && a.apply_gravity) ? 1 : 0;
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
     P.pf = tunables().rb_pf;
+    P.fast = tunables().rb_fast;
     dim3 grid((unsigned)((P.n_strips + 3) / 4), (unsigned)n_chunks);
     const bool full = k_act == KB;
     if (t == 0) { if (full) k_project_rb<KB, true, true><<<grid, 128, 0, stream>>>(P); else k_project_rb<KB, true, false><<<grid, 128, 0, stream>>>(P); }
