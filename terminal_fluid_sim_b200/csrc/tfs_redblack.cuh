@@ -22,7 +22,8 @@
 //   * strips and column chunks OVERLAP by NS rows / columns and recompute the overlap: a wrong value at the
 //     edge of what was loaded moves inwards by at most one cell per half-sweep, so after NS stages the
 //     inner 64 - 2*NS rows and Lx columns are exact.  No halo exchange, no cross-CTA dependency, and the
-//     same kernel serves x-slabs (the slab's NS stored halo columns are the chunk overlap).
+//     same kernel serves x-slabs (the slab's stored halo columns are the chunk overlap; the slab keeps NS + 2 of
+//     them because its outermost stored column has a wrong flag byte, see kHalo in tfs_api.cu).
 //   * warp-uniform fast path when every cell of a column's 64 rows is plain interior fluid (11 flops/cell).
 #pragma once
 #include "tfs_systolic.cuh"  // cell_update4
