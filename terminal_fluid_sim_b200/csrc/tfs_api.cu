@@ -313,6 +313,7 @@ void preload_step_kernels() {
     cudaFuncAttributes fa;
     const void *fns[] = {(const void *)tfs::k_cell_flags, (const void *)tfs::k_flag_wait2, (const void *)tfs::k_flag_set,
                          (const void *)tfs::k_copy_f4, (const void *)tfs::k_advect32<8, true, false>,
+                         (const void *)tfs::k_advect32_pair<4, 6, true, true>,
                          (const void *)tfs::k_project_rb<tfs::kRbKB, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true>,
                          (const void *)tfs::k_project_rb<tfs::kRbKB, true, false>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, false>,
                          (const void *)tfs::k_fill_f32, (const void *)tfs::k_fill_range_f32, (const void *)tfs::k_fill_range_u8,
@@ -543,13 +544,38 @@ int phase_advect(tfs_sim *s, float dt) {
     const bool fits32 = W * H < (1LL << 31) - (1LL << 20) && W < (1LL << 22) && H < (1LL << 22);
     const float4 dims = make_float4((float)W, (float)H, (float)(W - 1), (float)(H - 1));
     if (s->slab()) {
-        // owned columns only; pointers are rebased to global columns, halos supply the neighbours' cells
-        constexpr int CPB = 8;
+        // owned columns only; pointers are rebased to global columns, halos supply the neighbours' cells.  Samples that
+        // leave the stored columns (|vel|*dt beyond the halo: SURVEY H4) are loaded from the neighbours' memory:
+        // their pre-advection u, v, s stay intact until their next projection, which waits for this rank's pushB -
+        // the whole kernel of the right neighbour, but only the LAST band of the left one in the exact mode, whose
+        // earlier bands write columns below c_lo - 32 (tfs_systolic4.cuh): hence the bounded reach to the left.
         const long long sh = s->xs0 * H;
-        dim3 grid(blocks_for(H, 128), blocks_for(s->c_hi - s->c_lo, CPB));
-        tfs::k_advect32<CPB, true><<<grid, 128, 0, s->stream>>>(s->u - sh, s->v - sh, s->s - sh, s->flags - sh, s->u2 - sh, s->v2 - sh,
-                                                                 s->s2 - sh, (int)W, (int)H, dt, 1.0f, dims, (int)s->c_lo, (int)s->c_hi,
-                                                                 (unsigned)s->xs0, (unsigned)(s->xs0 + s->ncols - 1), s->d_oob);
+        tfs::SlabFar far;
+        far.cs0 = (unsigned)s->xs0; far.cs1 = (unsigned)(s->xs0 + s->ncols - 1); far.oob = s->d_oob;
+        const int fld[3] = {0, 1, 3};  // logical u, v, s
+        if (s->peerL.present) {
+            for (int f = 0; f < 3; ++f) far.L[f] = peer_logical(s, s->peerL, fld[f]) - s->peerL.xs0 * H;
+            const long long reach = s->opt.mode == TFS_MODE_RED_BLACK ? s->peerL.c_lo : std::max(s->peerL.c_lo, s->c_lo - 32);
+            far.l0 = (unsigned)reach; far.l1 = (unsigned)(s->peerL.c_hi - 1);
+        }
+        if (s->peerR.present) {
+            for (int f = 0; f < 3; ++f) far.R[f] = peer_logical(s, s->peerR, fld[f]) - s->peerR.xs0 * H;
+            far.r0 = (unsigned)s->peerR.c_lo; far.r1 = (unsigned)(s->peerR.c_hi - 1);
+        }
+        if (tunables().adv_pair && H % 256 == 0) {
+            constexpr int CPB = 4;
+            auto two = [](float x) { uint32_t b; memcpy(&b, &x, 4); return (tfs::f2)b | ((tfs::f2)b << 32); };
+            const tfs::F2K k{two(1.0f), two(-1.0f), two(-0.0f)};
+            dim3 grid((unsigned)(H / 256), blocks_for(s->c_hi - s->c_lo, CPB));
+            tfs::k_advect32_pair<CPB, 6, true, true><<<grid, 128, 0, s->stream>>>(s->u - sh, s->v - sh, s->s - sh, s->flags - sh, s->u2 - sh,
+                                                                                 s->v2 - sh, s->s2 - sh, (int)W, (int)H, two(dt), 1.0f, k,
+                                                                                 (int)s->c_lo, (int)s->c_hi, far);
+        } else {
+            constexpr int CPB = 8;
+            dim3 grid(blocks_for(H, 128), blocks_for(s->c_hi - s->c_lo, CPB));
+            tfs::k_advect32<CPB, true><<<grid, 128, 0, s->stream>>>(s->u - sh, s->v - sh, s->s - sh, s->flags - sh, s->u2 - sh, s->v2 - sh,
+                                                                     s->s2 - sh, (int)W, (int)H, dt, 1.0f, dims, (int)s->c_lo, (int)s->c_hi, far);
+        }
     } else if (fits32 && !adv_env) {
         // Two cells per thread with packed f32x2 arithmetic when the rows tile by 256 (k_advect32_pair), else one
         // cell per thread; both ask the L2 for their tile up front when the column segments are 16-byte aligned.
@@ -989,6 +1015,7 @@ int tfs_restart(tfs_sim *s) {
     // the identity and only the left border is rewritten; no reallocation needed.
     int rc = set_device(s);
     if (rc) return rc;
+    if (s->oob_pending) CU(cudaEventSynchronize(s->oob_ev));  // a copy of the flag still in flight must not land later
     CU(cudaMemsetAsync(s->d_oob, 0, sizeof(int), s->stream));
     if (s->h_oob) *s->h_oob = 0;
     s->oob_pending = false;

@@ -273,9 +273,27 @@ TFS_DEVINL float magic_float(float y, float one) { return __fmaf_rn(y, one, -TFS
 template <bool SLAB>
 TFS_DEVINL float ldf(const float *p) { return SLAB ? __ldcg(p) : __ldg(p); }
 
+// What an x-slab's advection can reach beyond its own stored columns [cs0, cs1]: the neighbours' memory, read
+// directly over NVLink (the back-trace distance |vel|*dt is unbounded, simulator.rs:211-212, so a halo of
+// fixed width is only the fast path).  L / R are the peers' pre-advection u, v, s rebased to GLOBAL columns; [l0, l1] and
+// [r0, r1] are the columns that are safe to read there (tfs_api.cu, step_slab); anything further sets *oob.
+struct SlabFar {
+    const float *L[3] = {nullptr, nullptr, nullptr}, *R[3] = {nullptr, nullptr, nullptr};
+    unsigned cs0 = 0u, cs1 = 0u, l0 = 1u, l1 = 0u, r0 = 1u, r1 = 0u;
+    int *oob = nullptr;
+};
+// one corner of a bilinear sample whose column may lie outside the stored range (rare: out of line)
+__device__ __noinline__ float far_load(const SlabFar &F, int ft, const float *__restrict__ local, unsigned col, unsigned row, unsigned H) {
+    if (col >= F.cs0 && col <= F.cs1) return __ldcg(local + (col * H + row));
+    if (F.L[ft] && col >= F.l0 && col <= F.l1) return __ldcg(F.L[ft] + (col * H + row));
+    if (F.R[ft] && col >= F.r0 && col <= F.r1) return __ldcg(F.R[ft] + (col * H + row));
+    *F.oob = 1;  // benign race: every writer stores 1
+    return __ldcg(local + (min(max(col, F.cs0), F.cs1) * H + row));
+}
+
 template <int FT, bool SLAB = false>
 TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, int W, int H, float Wf, float Hf,
-                                float one, unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
+                                float one, const SlabFar *far = nullptr) {
     const float dx = (FT == FT_U) ? 0.0f : 0.5f;   // simulator.rs:277-281
     const float dy = (FT == FT_V) ? 0.0f : 0.5f;
     x = fmaxf(fminf(x, Wf), 1.0f);                 // :271
@@ -289,19 +307,18 @@ TFS_DEVINL float sample_field32(const float *__restrict__ f, float x, float y, i
     const float ty = fsub_f(ys, magic_float(ym, one), one);            // :289
     const float sx = fsub_f(1.0f, tx, one), sy = fsub_f(1.0f, ty, one);  // :291-292
     // xr = min(xl+1, W-1), yt = min(yb+1, H-1) (:284, :288) as index offsets: +H / +1 unless clamped
-    unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
+    const unsigned dxo = (xl < (unsigned)(W - 1)) ? (unsigned)H : 0u;
     const unsigned dyo = (yb < (unsigned)(H - 1)) ? 1u : 0u;
-    unsigned xls = xl;
-    if (SLAB) {
-        if (xl < cs0 || xl + (dxo ? 1u : 0u) > cs1) {
-            *oob = 1;  // benign race: every writer stores 1
-            xls = min(max(xl, cs0), cs1);
-            if (xls + 1u > cs1) dxo = 0u;
-        }
+    float f00, f10, f11, f01;
+    const unsigned xr = xl + (dxo ? 1u : 0u);
+    if (SLAB && (xl < far->cs0 || xr > far->cs1)) {  // beyond the stored columns: the neighbours' memory
+        f00 = far_load(*far, FT, f, xl, yb, (unsigned)H); f10 = far_load(*far, FT, f, xr, yb, (unsigned)H);
+        f11 = far_load(*far, FT, f, xr, yb + dyo, (unsigned)H); f01 = far_load(*far, FT, f, xl, yb + dyo, (unsigned)H);
+    } else {
+        const unsigned i00 = xl * (unsigned)H + yb, i10 = i00 + dxo;
+        f00 = ldf<SLAB>(f + i00); f10 = ldf<SLAB>(f + i10);
+        f11 = ldf<SLAB>(f + i10 + dyo); f01 = ldf<SLAB>(f + i00 + dyo);
     }
-    const unsigned i00 = xls * (unsigned)H + yb, i10 = i00 + dxo;
-    const float f00 = ldf<SLAB>(f + i00), f10 = ldf<SLAB>(f + i10);
-    const float f11 = ldf<SLAB>(f + i10 + dyo), f01 = ldf<SLAB>(f + i00 + dyo);
     return fadd_f(fadd_f(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11), one),
                   fmul(fmul(sx, ty), f01), one);   // :294-297
 }
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(256)
 k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
            const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
            float *__restrict__ ns, int W, int H, float dt, float one, float4 dims, int c_begin = 0, int c_end = 0x7fffffff,
-           unsigned cs0 = 0u, unsigned cs1 = 0u, int *oob = nullptr) {
+           const __grid_constant__ SlabFar far = SlabFar()) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = c_begin + blockIdx.y * CPB;
     if (L2PF) prefetch_tile_l2(u, v, s, flags, W, H, i0, CPB, blockIdx.x * blockDim.x, min((int)blockDim.x, H - (int)(blockIdx.x * blockDim.x)));
@@ -406,9 +423,9 @@ k_advect32(const float *__restrict__ u, const float *__restrict__ v, const float
                 sn = sample_interior32<FT_S>(s, xsm, ysm, H, one);
             }
         } else if (live) {
-            un = sample_field32<FT_U, SLAB>(u, xu, yu, W, H, Wf, Hf, one, cs0, cs1, oob);
-            vn = sample_field32<FT_V, SLAB>(v, xv, yv, W, H, Wf, Hf, one, cs0, cs1, oob);
-            sn = sample_field32<FT_S, SLAB>(s, xsm, ysm, W, H, Wf, Hf, one, cs0, cs1, oob);
+            un = sample_field32<FT_U, SLAB>(u, xu, yu, W, H, Wf, Hf, one, &far);
+            vn = sample_field32<FT_V, SLAB>(v, xv, yv, W, H, Wf, Hf, one, &far);
+            sn = sample_field32<FT_S, SLAB>(s, xsm, ysm, W, H, Wf, Hf, one, &far);
         }
         nu[idx] = un; nv[idx] = vn; ns[idx] = sn;
         // march: column i+1 becomes the own column, column i the left one
@@ -445,7 +462,7 @@ TFS_DEVINL f2 mul2(f2 a, f2 b, const F2K &k) { return f2_fma(a, b, k.nzero); }
 // sample_vector on the clamp-free interior domain (see sample_interior32) for the cell pair.  Both
 // points must be inside [1, W-1) x [1, H-1) (also for a cell that is not live, whose result the
 // caller discards), so all eight loads are unconditional.
-template <int FT>
+template <int FT, bool SLAB = false>
 TFS_DEVINL f2 sample_interior_pair(const float *__restrict__ f, f2 x, f2 y, int H, const F2K &k) {
     const f2 mhalf = f2_pack(-0.5f, -0.5f);
     const f2 xs = (FT == FT_U) ? x : f2_fma(x, k.one, mhalf), ys = (FT == FT_V) ? y : f2_fma(y, k.one, mhalf);  // :277-281
@@ -457,8 +474,8 @@ TFS_DEVINL f2 sample_interior_pair(const float *__restrict__ f, f2 x, f2 y, int 
     const f2 sx = f2_fma(tx, k.mone, k.one), sy = f2_fma(ty, k.mone, k.one);                                 // :291-292
     const float *a0 = f + (xlA * (unsigned)H + ybA), *a1 = a0 + H;   // (xl, yb); the other corners are +H, +H+1, +1
     const float *b0 = f + (xlB * (unsigned)H + ybB), *b1 = b0 + H;
-    const f2 f00 = f2_pack(__ldg(a0), __ldg(b0)), f10 = f2_pack(__ldg(a1), __ldg(b1));
-    const f2 f11 = f2_pack(__ldg(a1 + 1), __ldg(b1 + 1)), f01 = f2_pack(__ldg(a0 + 1), __ldg(b0 + 1));
+    const f2 f00 = f2_pack(ldf<SLAB>(a0), ldf<SLAB>(b0)), f10 = f2_pack(ldf<SLAB>(a1), ldf<SLAB>(b1));
+    const f2 f11 = f2_pack(ldf<SLAB>(a1 + 1), ldf<SLAB>(b1 + 1)), f01 = f2_pack(ldf<SLAB>(a0 + 1), ldf<SLAB>(b0 + 1));
     const f2 t0 = mul2(mul2(sx, sy, k), f00, k), t1 = mul2(mul2(tx, sy, k), f10, k);
     const f2 t2 = mul2(mul2(tx, ty, k), f11, k), t3 = mul2(mul2(sx, ty, k), f01, k);
     return add2(add2(add2(t0, t1, k), t2, k), t3, k);   // :294-297
@@ -477,14 +494,15 @@ TFS_DEVINL bool in_range6(f2 a, f2 b, f2 c, unsigned lo_bits, unsigned hi_bits) 
 // the rare general path of one cell (clamps of simulator.rs:271-288 may bind), out of line to keep the
 // unrolled main loop small
 struct Uvs { float u, v, s; };
+template <bool SLAB>
 __device__ __noinline__ Uvs advect_general32(const float *__restrict__ u, const float *__restrict__ v,
                                              const float *__restrict__ s, int W, int H, float one, float xu, float yu,
-                                             float xv, float yv, float xsm, float ysm) {
+                                             float xv, float yv, float xsm, float ysm, const SlabFar *far) {
     const float Wf = (float)W, Hf = (float)H;
     Uvs r;
-    r.u = sample_field32<FT_U>(u, xu, yu, W, H, Wf, Hf, one);
-    r.v = sample_field32<FT_V>(v, xv, yv, W, H, Wf, Hf, one);
-    r.s = sample_field32<FT_S>(s, xsm, ysm, W, H, Wf, Hf, one);
+    r.u = sample_field32<FT_U, SLAB>(u, xu, yu, W, H, Wf, Hf, one, far);
+    r.v = sample_field32<FT_V, SLAB>(v, xv, yv, W, H, Wf, Hf, one, far);
+    r.s = sample_field32<FT_S, SLAB>(s, xsm, ysm, W, H, Wf, Hf, one, far);
     return r;
 }
 
@@ -493,37 +511,44 @@ __device__ __noinline__ Uvs advect_general32(const float *__restrict__ u, const 
 // A warp takes the clamp-free path when all 6 x 64 back-traced coordinates of its cells lie inside
 // [1, W-1) x [1, H-1) - cells that are not live included, so the warps holding the rows 0 / H-1 and
 // the columns 0 / W-1 always take the general path (about 3 % of the warps at 4096^2).
-template <int CPB, int MINB, bool L2PF>
+// SLAB: the pointers are global-column bases (storage pointer - xs0*H), the columns [c_begin, c_end) are advected and
+// the clamp-free path additionally requires every sample column to be stored (x in [cs0 + 1, cs1)).
+template <int CPB, int MINB, bool L2PF, bool SLAB = false>
 __global__ void __launch_bounds__(128, MINB)
 k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
                 const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
-                float *__restrict__ ns, int W, int H, f2 dt2, float one, F2K k) {
+                float *__restrict__ ns, int W, int H, f2 dt2, float one, F2K k, int c_begin = 0, int c_end = 0x7fffffff,
+                const __grid_constant__ SlabFar far = SlabFar()) {
     constexpr int RB = 128;  // row distance of the two cells
     const int jA = blockIdx.x * (2 * RB) + threadIdx.x, jB = jA + RB;
-    const int i0 = blockIdx.y * CPB;
-    if (L2PF) prefetch_tile_l2(u, v, s, flags, W, H, i0, CPB, blockIdx.x * (2 * RB), 2 * RB);
-    const unsigned one_bits = 0x3f800000u, wm1_bits = __float_as_uint((float)(W - 1)), hm1_bits = __float_as_uint((float)(H - 1));
+    const int i0 = c_begin + blockIdx.y * CPB;
+    const int c_stop = min(W, c_end);
+    if (L2PF) prefetch_tile_l2(u, v, s, flags, SLAB ? min(W, (int)far.cs1 + 1) : W, H, i0, min(CPB, c_stop - i0), blockIdx.x * (2 * RB), 2 * RB);
+    // x of every sample in [xlo, xhi): no clamp of simulator.rs:271-288 binds and (SLAB) both sample columns are stored
+    const unsigned xlo_bits = SLAB ? __float_as_uint((float)max(1, (int)far.cs0 + 1)) : 0x3f800000u;
+    const unsigned xhi_bits = __float_as_uint((float)(SLAB ? min(W - 1, (int)far.cs1) : W - 1));
+    const unsigned one_bits = 0x3f800000u, hm1_bits = __float_as_uint((float)(H - 1));
     const f2 half2 = f2_pack(0.5f, 0.5f), quarter2 = f2_pack(0.25f, 0.25f);
     const f2 fj = f2_pack((float)jA, (float)jB), fjh = add2(fj, half2, k);
     // row offsets of the (j-1) and (j+1) neighbours relative to row jA; clamped only for memory safety
     const int dAm = jA > 0 ? -1 : 0, dBp = RB + (jB < H - 1 ? 1 : 0);
     long long idx = (long long)i0 * H + jA;
     const float *pu = u + idx, *pv = v + idx;
-    f2 uC = f2_pack(pu[0], pu[RB]), vC = f2_pack(pv[0], pv[RB]);
-    f2 uB = f2_pack(pu[dAm], pu[RB - 1]), vT = f2_pack(pv[1], pv[dBp]);
+    f2 uC = f2_pack(ldf<SLAB>(pu), ldf<SLAB>(pu + RB)), vC = f2_pack(ldf<SLAB>(pv), ldf<SLAB>(pv + RB));
+    f2 uB = f2_pack(ldf<SLAB>(pu + dAm), ldf<SLAB>(pu + (RB - 1))), vT = f2_pack(ldf<SLAB>(pv + 1), ldf<SLAB>(pv + dBp));
     f2 vL = 0ull, vLT = 0ull;
-    if (i0 > 0) { vL = f2_pack(pv[-H], pv[RB - H]); vLT = f2_pack(pv[1 - H], pv[dBp - H]); }
+    if (i0 > 0) { vL = f2_pack(ldf<SLAB>(pv - H), ldf<SLAB>(pv + (RB - H))); vLT = f2_pack(ldf<SLAB>(pv + (1 - H)), ldf<SLAB>(pv + (dBp - H))); }
     f2 fi = f2_pack((float)i0, (float)i0);
 #pragma unroll
     for (int c = 0; c < CPB; ++c) {
         const int i = i0 + c;
-        if (i >= W) break;
+        if (i >= c_stop) break;
         const int hr = (i + 1 < W) ? H : 0;   // to column i+1; clamped for memory safety only
         const float *pur = u + idx + hr, *pvr = v + idx + hr, *ps = s + idx;
         const uint8_t *pf = flags + idx;
-        const f2 uR = f2_pack(pur[0], pur[RB]), uRB = f2_pack(pur[dAm], pur[RB - 1]);
-        const f2 vR = f2_pack(pvr[0], pvr[RB]), vRT = f2_pack(pvr[1], pvr[dBp]);
-        const float sA = ps[0], sB = ps[RB];
+        const f2 uR = f2_pack(ldf<SLAB>(pur), ldf<SLAB>(pur + RB)), uRB = f2_pack(ldf<SLAB>(pur + dAm), ldf<SLAB>(pur + (RB - 1)));
+        const f2 vR = f2_pack(ldf<SLAB>(pvr), ldf<SLAB>(pvr + RB)), vRT = f2_pack(ldf<SLAB>(pvr + 1), ldf<SLAB>(pvr + dBp));
+        const float sA = ldf<SLAB>(ps), sB = ldf<SLAB>(ps + RB);
         const bool liveA = (pf[0] & TFS_F_LIVE) != 0u, liveB = (pf[RB] & TFS_F_LIVE) != 0u;
         const f2 fih = add2(fi, half2, k);
         // back-traced positions (:207-236), same association as k_advect32
@@ -533,21 +558,21 @@ k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const 
         const f2 xu = sub2(fi, mul2(uC, dt2, k), k), yu = sub2(fjh, mul2(avg_v, dt2, k), k);
         const f2 xv = sub2(fih, mul2(avg_u, dt2, k), k), yv = sub2(fj, mul2(vC, dt2, k), k);
         const f2 xsm = sub2(fih, mul2(cu, dt2, k), k), ysm = sub2(fjh, mul2(cv, dt2, k), k);
-        const bool inside = in_range6(xu, xv, xsm, one_bits, wm1_bits) & in_range6(yu, yv, ysm, one_bits, hm1_bits);
+        const bool inside = in_range6(xu, xv, xsm, xlo_bits, xhi_bits) & in_range6(yu, yv, ysm, one_bits, hm1_bits);
         float unA = f2_lo(uC), unB = f2_hi(uC), vnA = f2_lo(vC), vnB = f2_hi(vC), snA = sA, snB = sB;
         if (__all_sync(0xffffffffu, inside)) {
-            const f2 un = sample_interior_pair<FT_U>(u, xu, yu, H, k);
-            const f2 vn = sample_interior_pair<FT_V>(v, xv, yv, H, k);
-            const f2 sn = sample_interior_pair<FT_S>(s, xsm, ysm, H, k);
+            const f2 un = sample_interior_pair<FT_U, SLAB>(u, xu, yu, H, k);
+            const f2 vn = sample_interior_pair<FT_V, SLAB>(v, xv, yv, H, k);
+            const f2 sn = sample_interior_pair<FT_S, SLAB>(s, xsm, ysm, H, k);
             if (liveA) { unA = f2_lo(un); vnA = f2_lo(vn); snA = f2_lo(sn); }
             if (liveB) { unB = f2_hi(un); vnB = f2_hi(vn); snB = f2_hi(sn); }
         } else {
             if (liveA) {
-                const Uvs r = advect_general32(u, v, s, W, H, one, f2_lo(xu), f2_lo(yu), f2_lo(xv), f2_lo(yv), f2_lo(xsm), f2_lo(ysm));
+                const Uvs r = advect_general32<SLAB>(u, v, s, W, H, one, f2_lo(xu), f2_lo(yu), f2_lo(xv), f2_lo(yv), f2_lo(xsm), f2_lo(ysm), &far);
                 unA = r.u; vnA = r.v; snA = r.s;
             }
             if (liveB) {
-                const Uvs r = advect_general32(u, v, s, W, H, one, f2_hi(xu), f2_hi(yu), f2_hi(xv), f2_hi(yv), f2_hi(xsm), f2_hi(ysm));
+                const Uvs r = advect_general32<SLAB>(u, v, s, W, H, one, f2_hi(xu), f2_hi(yu), f2_hi(xv), f2_hi(yv), f2_hi(xsm), f2_hi(ysm), &far);
                 unB = r.u; vnB = r.v; snB = r.s;
             }
         }

@@ -384,7 +384,14 @@ class SlabGroup:
                 if time.time() - t0 > timeout_s:
                     raise TimeoutError("x-slab step did not finish in %.0f s" % timeout_s)
                 time.sleep(0.002)
-        self.each("sync")
+        err = None
+        for s in self.sims:                                   # every slab is synchronised even if one reports an error
+            try:
+                s.sync()
+            except TfsError as e:
+                err = err or e
+        if err:
+            raise err
 
     def read_field(self, field):
         return np.concatenate([s.read_field(field) for s in self.sims])

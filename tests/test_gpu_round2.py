@@ -277,3 +277,37 @@ def test_cpp_mirror_frame_loop_computes_the_same_bits_as_the_ctypes_mirror():
         g.next_step(DT)
     assert got["checksum"] == ["%016x" % int(v) for v in g.checksum()]
     assert got["d2h_bytes_per_frame"] == 512 * 128 * 8 + 8
+
+
+# ---- advection reach beyond the halo on x-slabs ------------------------------------------------------
+@pytest.mark.parametrize("mode", [tfs.MODE_WAVEFRONT_EXACT, tfs.MODE_RED_BLACK])
+@pytest.mark.parametrize("H,amp", [(64, 1400.0), (256, 1400.0), (256, 300.0)])
+def test_slab_advection_reaches_into_the_neighbour_slab(mode, H, amp):
+    """|vel|*dt up to 23 columns: more than the 10 stored halo columns, so the samples are loaded from the neighbour's
+    memory (two slabs on one device; H = 256 takes the packed pair kernel, H = 64 the one-cell kernel)."""
+    W, K = 384, 8
+    grp = tfs.SlabGroup(W, H, world=2, devices=[0, 0], iterations=K, mode=mode)
+    o = OracleSim(W, H, iterations=K, mode=1 if mode == tfs.MODE_RED_BLACK else 0)
+    grp.each("fill_random_velocity", 31, amp); o.fill_random_velocity(31, amp)
+    for st in range(2):
+        grp.next_step(DT); o.step(DT)
+        grp.sync(timeout_s=60)
+        for f, n in ((tfs.FIELD_U, "u"), (tfs.FIELD_V, "v"), (tfs.FIELD_P, "p"), (tfs.FIELD_S, "s")):
+            a, b = grp.read_field(f), getattr(o, n)
+            assert bits_equal(a, b), f"mode {mode} H {H} amp {amp} step {st} {n}: " + first_mismatch(a, b, H)
+    grp.close()
+
+
+def test_slab_advection_beyond_the_reachable_columns_is_an_error_not_wrong_data():
+    """exact mode: the left neighbour may only be read 32 columns deep (its earlier bands already run the next step);
+    a back-trace of ~80 columns must surface as TFS_ERR_OUT_OF_RANGE at the next synchronising call"""
+    grp = tfs.SlabGroup(384, 64, world=2, devices=[0, 0], iterations=4)
+    grp.each("fill_random_velocity", 31, 5000.0)
+    grp.next_step(DT)
+    with pytest.raises(tfs.TfsError) as e:
+        grp.sync(timeout_s=60)
+    assert e.value.code == 2 and "back-trace" in str(e.value)
+    grp.each("restart_sim")                                   # clears the condition
+    grp.next_step(DT)
+    grp.sync(timeout_s=60)
+    grp.close()
