@@ -314,8 +314,8 @@ void preload_step_kernels() {
     const void *fns[] = {(const void *)tfs::k_cell_flags, (const void *)tfs::k_flag_wait2, (const void *)tfs::k_flag_set,
                          (const void *)tfs::k_copy_f4, (const void *)tfs::k_advect32<8, true, false>,
                          (const void *)tfs::k_advect32_pair<4, 6, true, true>,
-                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true>,
-                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, false>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, false>,
+                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true, true>,
+                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, false, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, false, true>,
                          (const void *)tfs::k_fill_f32, (const void *)tfs::k_fill_range_f32, (const void *)tfs::k_fill_range_u8,
                          (const void *)tfs::k_checksum, (const void *)tfs::k_minmax_partial, (const void *)tfs::k_minmax_final,
                          (const void *)tfs::k_div_partial, (const void *)tfs::k_pack_view<float>, (const void *)tfs::k_pack_view<uint8_t>,
@@ -408,6 +408,7 @@ int project_redblack_fused(tfs_sim *s, float omega, float pc, float gdt, bool fu
     a.W = (long long)s->W; a.H = (long long)s->H; a.xs0 = s->xs0; a.ncols = s->ncols; a.c_lo = s->c_lo; a.c_hi = s->c_hi;
     a.omega = omega; a.pc = pc; a.gdt = gdt; a.apply_gravity = fuse_gravity;
     a.chunk_len = tunables().rb_chunk;
+    a.slab = s->slab();
     for (int t = 0; t < passes; ++t) {
         const int k_act = std::min(KB, K - t * KB);
         cudaError_t e = tfs::redblack_pass(a, t, k_act, s->stream);
@@ -593,7 +594,12 @@ int phase_advect(tfs_sim *s, float dt) {
             case 1: TFS_PAIR_LAUNCH(8, 8) break;
             case 2: TFS_PAIR_LAUNCH(4, 7) break;
             case 3: TFS_PAIR_LAUNCH(8, 6) break;
-            case 4: TFS_PAIR_LAUNCH(16, 8) break;
+            case 5: { dim3 grid((unsigned)(H / 256), blocks_for(W, 4));
+                      tfs::k_advect32_pair<4, 8, true, false, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2,
+                                                                                             (int)W, (int)H, two(dt), 1.0f, k); } break;
+            case 6: { dim3 grid((unsigned)(H / 256), blocks_for(W, 4));
+                      tfs::k_advect32_pair<4, 8, false, false, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2,
+                                                                                              (int)W, (int)H, two(dt), 1.0f, k); } break;
             default: TFS_PAIR_LAUNCH(4, 8) break;
             }
 #undef TFS_PAIR_LAUNCH

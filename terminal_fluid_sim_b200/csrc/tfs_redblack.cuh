@@ -47,14 +47,17 @@ struct RbParams {
 };
 
 // FULL: all NS stages of the pass are active (every pass but a shorter last one), so no per-stage test is issued.
-template <int KB, bool FIRST, bool FULL>
+// CG: field loads bypass L1 (ld.global.cg) - x-slab handles, whose halo columns are rewritten between launches by
+// ANOTHER stream (the neighbour's push): a line kept in L1 from an earlier launch would be stale when two slabs share one
+// device.  A single-GPU handle reads through L1 (ld.global.nc), where the rows shared by adjacent strips hit.
+template <int KB, bool FIRST, bool FULL, bool CG>
 __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
     constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
     constexpr unsigned ALL_PLAIN = (1u << NS) - 1u;
     static_assert(V >= 8, "too many fused iterations for a 64-row strip");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * 4 + warp;
+    const int strip = blockIdx.x * (blockDim.x >> 5) + warp;
     if (strip >= P.n_strips) return;
     const int H = P.H, xs0 = P.xs0, ncols = P.ncols;
     const int rA = strip * V - NS + 2 * lane;             // lower row of this lane's pair (even)
@@ -82,11 +85,9 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         const int li = i - xs0;
         if (row_ok && (unsigned)li < (unsigned)ncols) {  // stored columns lie inside the grid
             const size_t o = (size_t)li * (size_t)H + row_off;
-            // ld.global.cg: the halo columns of a slab are rewritten between launches by ANOTHER stream (the neighbour's
-            // push); a line kept in L1 from an earlier launch would be stale when two slabs share one device
-            r.u = __ldcg(reinterpret_cast<const float2 *>(P.in_u + o));
-            r.v = __ldcg(reinterpret_cast<const float2 *>(P.in_v + o));
-            if (!FIRST) r.p = __ldcg(reinterpret_cast<const float2 *>(P.in_p + o));
+            r.u = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_u + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_u + o));
+            r.v = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_v + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_v + o));
+            if (!FIRST) r.p = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_p + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_p + o));
             r.f = __ldg(reinterpret_cast<const unsigned short *>(P.flags + o));
             if (FIRST && P.apply_gravity) {
                 if (r.f & TFS_F_LIVE) r.v.x = fadd(r.v.x, P.gdt);
@@ -209,6 +210,7 @@ struct RbLaunchArgs {
     long long W, H, xs0, ncols, c_lo, c_hi;
     float omega, pc, gdt;
     bool apply_gravity;
+    bool slab;             // x-slab handle: loads bypass L1
     int chunk_len;         // 0 = default
 };
 
@@ -234,10 +236,21 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
     P.pf = tunables().rb_pf;
     P.fast = tunables().rb_fast;
-    dim3 grid((unsigned)((P.n_strips + 3) / 4), (unsigned)n_chunks);
-    const bool full = k_act == KB;
-    if (t == 0) { if (full) k_project_rb<KB, true, true><<<grid, 128, 0, stream>>>(P); else k_project_rb<KB, true, false><<<grid, 128, 0, stream>>>(P); }
-    else { if (full) k_project_rb<KB, false, true><<<grid, 128, 0, stream>>>(P); else k_project_rb<KB, false, false><<<grid, 128, 0, stream>>>(P); }
+    // 4 warps (adjacent strips) per CTA: their overlapping rows hit L1; 1 or 2 warps per CTA balance a one-wave launch
+    // better but measured 1-5 % slower at 4096^2 and 16384^2
+    const int wpc = tunables().rb_wpc == 1 ? 1 : (tunables().rb_wpc == 2 ? 2 : 4);
+    dim3 grid((unsigned)((P.n_strips + wpc - 1) / wpc), (unsigned)n_chunks);
+    const unsigned bs = 32u * wpc;
+    const bool full = k_act == KB, first = t == 0;
+#define TFS_RB_LAUNCH(FIRST_, FULL_, CG_) k_project_rb<KB, FIRST_, FULL_, CG_><<<grid, bs, 0, stream>>>(P)
+    if (a.slab) {
+        if (first) { if (full) TFS_RB_LAUNCH(true, true, true); else TFS_RB_LAUNCH(true, false, true); }
+        else { if (full) TFS_RB_LAUNCH(false, true, true); else TFS_RB_LAUNCH(false, false, true); }
+    } else {
+        if (first) { if (full) TFS_RB_LAUNCH(true, true, false); else TFS_RB_LAUNCH(true, false, false); }
+        else { if (full) TFS_RB_LAUNCH(false, true, false); else TFS_RB_LAUNCH(false, false, false); }
+    }
+#undef TFS_RB_LAUNCH
     return cudaGetLastError();
 }
 

@@ -311,3 +311,29 @@ def test_slab_advection_beyond_the_reachable_columns_is_an_error_not_wrong_data(
     grp.next_step(DT)
     grp.sync(timeout_s=60)
     grp.close()
+
+
+# ---- hand-derived known answers (tests/kat.py) on the device -------------------------------------------------------
+@pytest.mark.parametrize("H", [8, 16, 256])
+def test_advection_and_sample_vector_known_answers_on_device(H):
+    """values worked by hand from simulator.rs:192-298 (tests/kat.py), independent of both CPU restatements; H = 8 runs the
+    one-cell kernel, 16 its L2-prefetching instantiation, 256 the packed two-cell kernel"""
+    from tests import kat
+    for name, (u, v, sm), expect in kat.advection_cases(H):
+        g = tfs.FluidSim(8, H)
+        g.write_field(tfs.FIELD_U, u); g.write_field(tfs.FIELD_V, v); g.write_field(tfs.FIELD_S, sm)
+        g.phase_advect(kat.DT16)
+        for f, x, y, want in expect:
+            got = float(getattr(g, f)[x * H + y])
+            assert got == want, f"{name} (H={H}): {f}[{x},{y}] = {got!r}, by hand {want!r}"
+
+
+def test_smoke_pipe_and_wind_column_known_answers_on_device():
+    from tests import kat
+    for H, size, lo, hi in kat.SMOKE_PIPE:
+        g = tfs.FluidSim(5, H, tfs.SimConfig(smoke_size=size, wind_speed=12.5))
+        want = np.ones((5, H), np.float32)
+        want[0, lo:hi] = 0.0
+        assert np.array_equal(g.get_smoke_grid().reshape(5, H), want), (H, size)
+        u = g.u.reshape(5, H)
+        assert np.all(u[1] == np.float32(12.5)) and np.count_nonzero(u) == H

@@ -157,3 +157,30 @@ def test_redblack_variant_converges_to_same_flow_class():
         b.step(DT)
     assert np.max(np.abs(a.u - b.u)) < 0.25 * 50.0
     assert abs(a.divergence_linf() - b.divergence_linf()) < 50.0
+
+
+# ---- hand-derived known answers (tests/kat.py): they pin BOTH restatements to the source text ----------------------
+from tests import kat
+
+
+@pytest.mark.parametrize("H", [8, 256])
+def test_advection_and_sample_vector_known_answers(H):
+    for name, (u, v, sm), expect in kat.advection_cases(H):
+        for make in (lambda: OracleSim(8, H), lambda: NpSim(8, H)):
+            o = make()
+            o.u[:], o.v[:], o.s[:] = u, v, sm
+            o.move_velocity(kat.DT16)
+            for f, x, y, want in expect:
+                got = float(getattr(o, f)[x * H + y])
+                assert got == want, f"{type(o).__name__} {name}: {f}[{x},{y}] = {got!r}, by hand {want!r}"
+
+
+@pytest.mark.parametrize("H,size,lo,hi", kat.SMOKE_PIPE)
+def test_smoke_pipe_and_wind_column_known_answers(H, size, lo, hi):
+    for o in (OracleSim(5, H, smoke_size=size, wind_speed=12.5), NpSim(5, H, smoke_size=size, wind_speed=12.5)):
+        s = np.array(o.s).reshape(5, H)
+        want = np.ones((5, H), np.float32)
+        want[0, lo:hi] = 0.0
+        assert np.array_equal(s, want), (type(o).__name__, H, size)
+        u = np.array(o.u).reshape(5, H)
+        assert np.all(u[1] == np.float32(12.5)) and np.count_nonzero(u) == H
