@@ -314,8 +314,7 @@ void preload_step_kernels() {
     const void *fns[] = {(const void *)tfs::k_cell_flags, (const void *)tfs::k_flag_wait2, (const void *)tfs::k_flag_set,
                          (const void *)tfs::k_copy_f4, (const void *)tfs::k_advect32<8, true, false>,
                          (const void *)tfs::k_advect32_pair<4, 6, true, true>,
-                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true, true>,
-                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, false, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, false, true>,
+                         (const void *)tfs::k_project_rb<tfs::kRbKB, true, true>, (const void *)tfs::k_project_rb<tfs::kRbKB, false, true>,
                          (const void *)tfs::k_fill_f32, (const void *)tfs::k_fill_range_f32, (const void *)tfs::k_fill_range_u8,
                          (const void *)tfs::k_checksum, (const void *)tfs::k_minmax_partial, (const void *)tfs::k_minmax_final,
                          (const void *)tfs::k_div_partial, (const void *)tfs::k_pack_view<float>, (const void *)tfs::k_pack_view<uint8_t>,

@@ -107,7 +107,6 @@ struct Tunables {
     int adv_variant = 0;          // TFS_ADV_VARIANT = n: experimental advection variants
     int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
     int rb_pf = 4;                // TFS_RB_PF = n: L2 prefetch distance (columns) of the fused red-black kernel
-    int rb_fast = 1;              // TFS_RB_FAST = 0: never take the all-plain straight-line step
     int rb_wpc = 4;               // TFS_RB_WPC = 1 / 2 / 4: warps per CTA of the fused red-black kernel
     int rb_chunk = 0;             // TFS_RB_CHUNK = n: columns per chunk of the fused red-black kernel (0 = default)
     const char *task_trace_prefix = nullptr;
@@ -128,7 +127,6 @@ inline const Tunables &tunables() {
         x.rb_variant = geti("TFS_RB_VARIANT", 0);
         x.rb_chunk = geti("TFS_RB_CHUNK", 0);
         x.rb_pf = geti("TFS_RB_PF", 4);
-        x.rb_fast = geti("TFS_RB_FAST", 1);
         x.rb_wpc = geti("TFS_RB_WPC", 4);
         x.task_trace_prefix = getenv("TFS_TASK_TRACE_PREFIX");
         return x;

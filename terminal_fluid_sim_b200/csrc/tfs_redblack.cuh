@@ -24,7 +24,12 @@
 //     inner 64 - 2*NS rows and Lx columns are exact.  No halo exchange, no cross-CTA dependency, and the
 //     same kernel serves x-slabs (the slab's stored halo columns are the chunk overlap; the slab keeps NS + 2 of
 //     them because its outermost stored column has a wrong flag byte, see kHalo in tfs_api.cu).
-//   * warp-uniform fast path when every cell of a column's 64 rows is plain interior fluid (11 flops/cell).
+//   * warp-uniform fast update when every cell of a column's 64 rows is plain interior fluid (11 flops/cell).
+//     Measured and rejected (same B200, 4096^2 K=100 / 32768^2 2 % obstacles K=200, ms per projection): a straight-
+//     line step for an all-plain window 4.73 / 745 and an instantiation without the per-stage "stage active" test
+//     4.85 / 684 against 4.63 / 660 for this form; the general update out of line (__noinline__) 6.9 / 948.  The
+//     unrolled march loop is ~64 KB of code for 20 unsynchronised warps per SM: instruction fetch, not arithmetic,
+//     decides between these variants.
 #pragma once
 #include "tfs_systolic.cuh"  // cell_update4
 
@@ -41,20 +46,17 @@ struct RbParams {
     int chunk0, lx;      // first column chunk (global index), chunk length (multiple of NS)
     int ns_act;          // active stages of this pass (2 * iterations fused in it)
     int pf;              // L2 prefetch distance in columns (0 = none)
-    int fast;            // 1: straight-line step when the whole window is plain fluid
     int apply_gravity;   // first pass: v += gdt on updatable cells while loading (simulator.rs:137-149)
     float omega, pc, gdt;
 };
 
-// FULL: all NS stages of the pass are active (every pass but a shorter last one), so no per-stage test is issued.
 // CG: field loads bypass L1 (ld.global.cg) - x-slab handles, whose halo columns are rewritten between launches by
 // ANOTHER stream (the neighbour's push): a line kept in L1 from an earlier launch would be stale when two slabs share one
 // device.  A single-GPU handle reads through L1 (ld.global.nc), where the rows shared by adjacent strips hit.
-template <int KB, bool FIRST, bool FULL, bool CG>
+template <int KB, bool FIRST, bool CG>
 __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
     constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
-    constexpr unsigned ALL_PLAIN = (1u << NS) - 1u;
     static_assert(V >= 8, "too many fused iterations for a 64-row strip");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     const bool store_lane = row_ok && lane >= KB && lane < 32 - KB;
     const int gx0 = (P.chunk0 + (int)blockIdx.y) * P.lx;  // first column this chunk finalises
     const int vx0 = max(gx0, P.c_lo), vx1 = min(gx0 + P.lx, P.c_hi);
-    const int ns_act = FULL ? NS : P.ns_act;
+    const int ns_act = P.ns_act;
     const float omega = P.omega, pc = P.pc;
 
     // register window: slot c holds column i with i % NS == c (rows A = lower, B = upper)
@@ -135,35 +137,10 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
             // (i & 1) == (s & 1), i.e. when m is odd -- a compile-time fact of the unrolled step
             constexpr int dummy = 0; (void)dummy;
             const bool lower = (m & 1) != 0;
-            if (FULL && P.fast && plain == ALL_PLAIN) {
-                // every cell the NS stages touch is plain interior fluid: straight-line code, no flag work at all
-                if (lower) {
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const int c = (m - 1 - s + 2 * NS) % NS, cn = (c + 1) % NS;
-                        float &uR = (s == 0) ? pend.u.x : uA[cn];
-                        cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
-                    }
-                } else {
-                    float vT[NS];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) vT[s] = __shfl_down_sync(0xffffffffu, vA[(m - 1 - s + 2 * NS) % NS], 1);
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const int c = (m - 1 - s + 2 * NS) % NS, cn = (c + 1) % NS;
-                        float &uR = (s == 0) ? pend.u.y : uB[cn];
-                        cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT[s], pB[c]);
-                    }
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const float t = __shfl_up_sync(0xffffffffu, vT[s], 1);
-                        if (lane > 0) vA[(m - 1 - s + 2 * NS) % NS] = t;
-                    }
-                }
-            } else {
+            {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    if (FULL || s < ns_act) {
+                    if (s < ns_act) {
                         const int c = (m - 1 - s + 2 * NS) % NS;  // slot of column x-1-s
                         const int cn = (c + 1) % NS;              // slot of column x-s (s == 0: the pending column)
                         const bool is_plain = (plain >> c) & 1u;
@@ -228,29 +205,29 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.flags = a.flags;
     P.W = (int)a.W; P.H = (int)a.H; P.xs0 = (int)a.xs0; P.ncols = (int)a.ncols; P.c_lo = (int)a.c_lo; P.c_hi = (int)a.c_hi;
     P.n_strips = (int)((a.H + V - 1) / V);
-    P.lx = a.chunk_len > 0 ? (a.chunk_len + NS - 1) / NS * NS : 128;
+    // Chunk length: every warp marches lx + 2*NS columns to finalise lx of them, so long chunks waste less, but a grid
+    // that yields fewer warps than the GPU holds (148 SMs x 20) runs them at single-warp latency: take the shortest
+    // chunk that still fits in one wave, 128 columns at most.
+    int lx = 128;
+    if (a.chunk_len > 0) lx = (a.chunk_len + NS - 1) / NS * NS;
+    else
+        for (int c = 2 * NS; c < 128; c *= 2)
+            if ((long long)P.n_strips * ((a.c_hi - a.c_lo + c - 1) / c) <= 148LL * 20) { lx = c; break; }
+    P.lx = lx;
     P.chunk0 = (int)(a.c_lo / P.lx);
     const int n_chunks = (int)((a.c_hi + P.lx - 1) / P.lx) - P.chunk0;
     P.ns_act = 2 * k_act;
     P.apply_gravity = (t == 0 && a.apply_gravity) ? 1 : 0;
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
     P.pf = tunables().rb_pf;
-    P.fast = tunables().rb_fast;
     // 4 warps (adjacent strips) per CTA: their overlapping rows hit L1; 1 or 2 warps per CTA balance a one-wave launch
     // better but measured 1-5 % slower at 4096^2 and 16384^2
     const int wpc = tunables().rb_wpc == 1 ? 1 : (tunables().rb_wpc == 2 ? 2 : 4);
     dim3 grid((unsigned)((P.n_strips + wpc - 1) / wpc), (unsigned)n_chunks);
     const unsigned bs = 32u * wpc;
-    const bool full = k_act == KB, first = t == 0;
-#define TFS_RB_LAUNCH(FIRST_, FULL_, CG_) k_project_rb<KB, FIRST_, FULL_, CG_><<<grid, bs, 0, stream>>>(P)
-    if (a.slab) {
-        if (first) { if (full) TFS_RB_LAUNCH(true, true, true); else TFS_RB_LAUNCH(true, false, true); }
-        else { if (full) TFS_RB_LAUNCH(false, true, true); else TFS_RB_LAUNCH(false, false, true); }
-    } else {
-        if (first) { if (full) TFS_RB_LAUNCH(true, true, false); else TFS_RB_LAUNCH(true, false, false); }
-        else { if (full) TFS_RB_LAUNCH(false, true, false); else TFS_RB_LAUNCH(false, false, false); }
-    }
-#undef TFS_RB_LAUNCH
+    const bool first = t == 0;
+    if (a.slab) { if (first) k_project_rb<KB, true, true><<<grid, bs, 0, stream>>>(P); else k_project_rb<KB, false, true><<<grid, bs, 0, stream>>>(P); }
+    else { if (first) k_project_rb<KB, true, false><<<grid, bs, 0, stream>>>(P); else k_project_rb<KB, false, false><<<grid, bs, 0, stream>>>(P); }
     return cudaGetLastError();
 }
 
