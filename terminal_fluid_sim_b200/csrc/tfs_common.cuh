@@ -104,7 +104,6 @@ struct Tunables {
     int sys_grid = 0;             // TFS_SYS_GRID = n (cap on resident CTAs), -1 = "even"
     bool adv_pair = true;         // TFS_ADV_PAIR = 0: one-cell advection kernel
     char advect = 0;              // TFS_ADVECT = vec4 / scalar: generic advection kernels
-    int adv_variant = 0;          // TFS_ADV_VARIANT = n: experimental advection variants
     int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
     int rb_pf = 4;                // TFS_RB_PF = n: L2 prefetch distance (columns) of the fused red-black kernel
     int rb_wpc = 4;               // TFS_RB_WPC = 1 / 2 / 4: warps per CTA of the fused red-black kernel
@@ -123,7 +122,6 @@ inline const Tunables &tunables() {
         if (const char *e = getenv("TFS_SYS_GRID")) x.sys_grid = e[0] == 'e' ? -1 : atoi(e);
         x.adv_pair = geti("TFS_ADV_PAIR", 1) != 0;
         if (const char *e = getenv("TFS_ADVECT")) x.advect = e[0];
-        x.adv_variant = geti("TFS_ADV_VARIANT", 0);
         x.rb_variant = geti("TFS_RB_VARIANT", 0);
         x.rb_chunk = geti("TFS_RB_CHUNK", 0);
         x.rb_pf = geti("TFS_RB_PF", 4);

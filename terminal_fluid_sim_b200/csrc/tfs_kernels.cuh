@@ -513,11 +513,7 @@ __device__ __noinline__ Uvs advect_general32(const float *__restrict__ u, const 
 // the columns 0 / W-1 always take the general path (about 3 % of the warps at 4096^2).
 // SLAB: the pointers are global-column bases (storage pointer - xs0*H), the columns [c_begin, c_end) are advected and
 // the clamp-free path additionally requires every sample column to be stored (x in [cs0 + 1, cs1)).
-// L1PF: every lane of a warp asks the L1 for one line of the warp's tile up front (prefetch.global.L1): the lanes
-// enumerate {u, v} x {columns i0-1 .. i0+CPB} x {rows of cell A, rows of cell B} and {s} x {columns i0 .. i0+CPB-1} x
-// {A, B} - 32 lines for CPB = 4, one instruction.  The march's own loads and nearly all bilinear gathers then hit L1
-// instead of paying an L2 round trip twice per column.
-template <int CPB, int MINB, bool L2PF, bool SLAB = false, bool L1PF = false>
+template <int CPB, int MINB, bool L2PF, bool SLAB = false>
 __global__ void __launch_bounds__(128, MINB)
 k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ s,
                 const uint8_t *__restrict__ flags, float *__restrict__ nu, float *__restrict__ nv,
@@ -528,18 +524,6 @@ k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const 
     const int i0 = c_begin + blockIdx.y * CPB;
     const int c_stop = min(W, c_end);
     if (L2PF) prefetch_tile_l2(u, v, s, flags, SLAB ? min(W, (int)far.cs1 + 1) : W, H, i0, min(CPB, c_stop - i0), blockIdx.x * (2 * RB), 2 * RB);
-    if (L1PF) {
-        const int lane = threadIdx.x & 31, row0 = blockIdx.x * (2 * RB) + (threadIdx.x & ~31);  // first row of the warp's A cells
-        const int half = lane & 1, q = lane >> 1;                                               // A / B rows, combination index 0..15
-        const float *base = nullptr;
-        int col = 0;
-        if (q < 2 * (CPB + 2)) { base = (q & 1) ? v : u; col = i0 - 1 + (q >> 1); }            // u, v: columns i0-1 .. i0+CPB
-        else if (q < 2 * (CPB + 2) + CPB) { base = s; col = i0 + (q - 2 * (CPB + 2)); }         // s: columns i0 .. i0+CPB-1
-        if (base && col >= 0 && col < W) {
-            const float *ptr = base + ((long long)col * H + row0 + half * RB);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-        }
-    }
     // x of every sample in [xlo, xhi): no clamp of simulator.rs:271-288 binds and (SLAB) both sample columns are stored
     const unsigned xlo_bits = SLAB ? __float_as_uint((float)max(1, (int)far.cs0 + 1)) : 0x3f800000u;
     const unsigned xhi_bits = __float_as_uint((float)(SLAB ? min(W - 1, (int)far.cs1) : W - 1));
