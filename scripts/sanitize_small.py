@@ -1,6 +1,6 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck): exits non-zero on a parity failure."""
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import terminal_fluid_sim_b200 as tfs
 from oracle.oracle import OracleSim, frac_to_threshold
 dt = float(np.float32(1/60))

@@ -1,6 +1,6 @@
 """torchrun check: one process per GPU, IPC peer mappings; every rank compares its slab with the oracle."""
 import os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import terminal_fluid_sim_b200 as tfs
 from oracle.oracle import OracleSim, frac_to_threshold

@@ -1,7 +1,7 @@
 """torchrun, with a library built with TFS_NVCC_EXTRA=-DTFS_TASK_TRACE: per-task start/end times of the
 projection kernel of the LAST step on every rank (who runs when, how long tasks take, how busy the slots are)."""
 import os, sys, struct, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import terminal_fluid_sim_b200 as tfs
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
