@@ -1,5 +1,5 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck): exits non-zero on a parity failure."""
-import sys, numpy as np
+import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import terminal_fluid_sim_b200 as tfs
 from oracle.oracle import OracleSim, frac_to_threshold
