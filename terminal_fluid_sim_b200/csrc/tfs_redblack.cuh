@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
     constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
     static_assert(V >= 8, "too many fused iterations for a 64-row strip");
+    __shared__ float4 lut[32];  // cell_update_lut's table (tfs_systolic.cuh)
+    nb_lut_fill(lut, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * (blockDim.x >> 5) + warp;
     if (strip >= P.n_strips) return;
@@ -147,12 +150,12 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
                         if (lower) {
                             float &uR = (s == 0) ? pend.u.x : uA[cn];
                             if (is_plain) cell_update4<0>(15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
-                            else cell_update4<2>(fl[c] & 15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
+                            else cell_update_lut(lut, fl[c] & 15u, omega, pc, uA[c], uR, vA[c], vB[c], pA[c]);
                         } else {
                             float &uR = (s == 0) ? pend.u.y : uB[cn];
                             float vT = __shfl_down_sync(0xffffffffu, vA[c], 1);  // lane 31: its own value, inside the overlap
                             if (is_plain) cell_update4<0>(15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
-                            else cell_update4<2>((fl[c] >> 8) & 15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
+                            else cell_update_lut(lut, (fl[c] >> 8) & 15u, omega, pc, uB[c], uR, vB[c], vT, pB[c]);
                             vT = __shfl_up_sync(0xffffffffu, vT, 1);
                             if (lane > 0) vA[c] = vT;
                         }

@@ -137,6 +137,48 @@ TFS_DEVINL void cell_update4(unsigned nb, float omega, float pc, float &uC, floa
     uC = on ? a : uC; uR = on ? r : uR; vC = on ? c : vC; vT = on ? d : vT; p = on ? pp : p;
 }
 
+// The general update with its per-cell constants taken from a 16-entry table in shared memory, indexed by the four
+// neighbour bits: entry nb = two float4 {RN(1/n), -n, sL, sR} {sB, sT, -, -} (n = popcount, s* = 1.0 / +0.0).  This
+// replaces popc, int-to-float, the 1/n selection and four 0/1 selects per cell by two LDS.128, and the five "keep the
+// old value when the cell is not updated" selects by ONE: entry 0 holds {1, -1, +0, -0} {+0, -0} and the correction of
+// such a cell is forced to 1.0, so that every face update adds -0.0 (fma(-1, +0, x) and fma(1, -0, x)), which is the
+// identity for every x including both zeros and NaN.  Same arithmetic as cell_update4<2> for every other entry.
+// ~23 instructions per cell instead of ~41: the exact kernel is issue-bound where obstacles are dense (config 5).
+TFS_DEVINL void nb_lut_fill(float4 *lut, int tid, int nthreads) {
+    for (int nb = tid; nb < 16; nb += nthreads) {
+        const int n = __popc(nb);
+        const float rcp = (n == 3) ? 0.333333343267440796f : ((n == 4) ? 0.25f : ((n == 2) ? 0.5f : 1.0f));
+        if (nb == 0) {
+            lut[0] = make_float4(1.0f, -1.0f, 0.0f, -0.0f);
+            lut[1] = make_float4(0.0f, -0.0f, 0.0f, 0.0f);
+        } else {
+            lut[2 * nb] = make_float4(rcp, -(float)n, (nb & TFS_F_L) ? 1.0f : 0.0f, (nb & TFS_F_R) ? 1.0f : 0.0f);
+            lut[2 * nb + 1] = make_float4((nb & TFS_F_B) ? 1.0f : 0.0f, (nb & TFS_F_T) ? 1.0f : 0.0f, 0.0f, 0.0f);
+        }
+    }
+}
+TFS_DEVINL void cell_update_lut(const float4 *__restrict__ lut, unsigned nb, float omega, float pc, float &uC, float &uR, float &vC,
+                                float &vT, float &p) {
+    const float4 A = lut[2 * nb];
+    const float2 B = *reinterpret_cast<const float2 *>(&lut[2 * nb + 1]);
+    const float div = fsub(fadd(fsub(uR, uC), vT), vC);        // :176-178
+    const float x = -div;
+    // div_small(x, n, RN(1/n)) (tfs_common.cuh): exact IEEE x / n
+    const float q0 = __fmul_rn(x, A.x);
+    const float rr = __fmaf_rn(A.y, q0, x);
+    float q = __fmaf_rn(rr, A.x, q0);
+    q = (fabsf(q0) <= 3.402823466e38f && q0 != 0.0f) ? q : q0;
+    const float corr = fmul(omega, q);                         // :180
+    const bool on = nb != 0u;                                  // :161, :172
+    const float ce = on ? corr : 1.0f;
+    uC = __fmaf_rn(-ce, A.z, uC);                              // :181
+    uR = __fmaf_rn(ce, A.w, uR);                               // :182
+    vC = __fmaf_rn(-ce, B.x, vC);                              // :184
+    vT = __fmaf_rn(ce, B.y, vT);                               // :185
+    const float pp = fadd(p, fmul(pc, corr));                  // :186
+    p = on ? pp : p;
+}
+
 // optional per-segment cycle accounting of the compute warps (-DTFS_SYS_TRACE; debugging aid only)
 #ifdef TFS_SYS_TRACE
 #define TFS_TR_DECL long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64();
