@@ -143,7 +143,9 @@ TFS_DEVINL void cell_update4(unsigned nb, float omega, float pc, float &uC, floa
 // old value when the cell is not updated" selects by ONE: entry 0 holds {1, -1, +0, -0} {+0, -0} and the correction of
 // such a cell is forced to 1.0, so that every face update adds -0.0 (fma(-1, +0, x) and fma(1, -0, x)), which is the
 // identity for every x including both zeros and NaN.  Same arithmetic as cell_update4<2> for every other entry.
-// ~23 instructions per cell instead of ~41: the exact kernel is issue-bound where obstacles are dense (config 5).
+// ~25 instructions per cell instead of ~41.  Used by the red-black kernel (config 5, 2 % obstacles: 660 -> 586 ms per
+// projection).  In the exact block-ring kernel it gained 1 % at config 5 and LOST 6-8 % on obstacle-free grids (the
+// plain path was scheduled differently around it), so that kernel keeps cell_update4<2>.
 TFS_DEVINL void nb_lut_fill(float4 *lut, int tid, int nthreads) {
     for (int nb = tid; nb < 16; nb += nthreads) {
         const int n = __popc(nb);

@@ -113,7 +113,6 @@ struct Sys4Smem {
     unsigned long long rec_full[NR], rec_empty[NR];
     unsigned long long rec_written[NPH], pub_done[NPH];
     unsigned long long out_empty[NS_OUT];
-    float4 lut[32];  // cell_update_lut's table
     int task;
 };
 
@@ -141,7 +140,6 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
 #ifdef TFS_TASK_TRACE
     int tt_prev = -1;
 #endif
-    nb_lut_fill(sm.lut, threadIdx.x, blockDim.x);  // made visible by the first __syncthreads of the task loop
     for (;;) {
         __syncthreads();  // previous task fully retired (smem and mbarrier reuse)
         if (threadIdx.x == 0) {
@@ -518,7 +516,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < KG; ++kk)
-                        cell_update_lut(sm.lut, (fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
+                        cell_update4<2>((fl_eff >> (4 * kk)) & 15u, P.omega, P.pc, a[kk], r[kk], cv[kk], d[kk], pp[kk]);
                 }
                 // a = uCf (u of the cell after iteration k), r = uRp, cv = vCf, d = vTp, pp = pout
                 TFS_TR(2)
