@@ -106,6 +106,7 @@ struct Tunables {
     char advect = 0;              // TFS_ADVECT = vec4 / scalar: generic advection kernels
     int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
     int rb_pf = 4;                // TFS_RB_PF = n: L2 prefetch distance (columns) of the fused red-black kernel
+    int rb_sync = 1;              // TFS_RB_SYNC = 0: no per-step barrier in the fused red-black kernel
     int rb_wpc = 4;               // TFS_RB_WPC = 1 / 2 / 4: warps per CTA of the fused red-black kernel
     int rb_chunk = 0;             // TFS_RB_CHUNK = n: columns per chunk of the fused red-black kernel (0 = default)
     const char *task_trace_prefix = nullptr;
@@ -126,6 +127,7 @@ inline const Tunables &tunables() {
         x.rb_chunk = geti("TFS_RB_CHUNK", 0);
         x.rb_pf = geti("TFS_RB_PF", 4);
         x.rb_wpc = geti("TFS_RB_WPC", 4);
+        x.rb_sync = geti("TFS_RB_SYNC", 1);
         x.task_trace_prefix = getenv("TFS_TASK_TRACE_PREFIX");
         return x;
     }();

@@ -46,6 +46,7 @@ struct RbParams {
     int chunk0, lx;      // first column chunk (global index), chunk length (multiple of NS)
     int ns_act;          // active stages of this pass (2 * iterations fused in it)
     int pf;              // L2 prefetch distance in columns (0 = none)
+    int step_sync;       // 1: the CTA's warps meet at a barrier after every march step
     int apply_gravity;   // first pass: v += gdt on updatable cells while loading (simulator.rs:137-149)
     float omega, pc, gdt;
 };
@@ -63,10 +64,11 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (strip >= P.n_strips) return;
     const int H = P.H, xs0 = P.xs0, ncols = P.ncols;
     const int rA = strip * V - NS + 2 * lane;             // lower row of this lane's pair (even)
-    const bool row_ok = rA >= 0 && rA < H;                // H is even: the pair is inside or outside together
+    // H is even: the pair is inside or outside together.  (A warp past the last strip marches along with all rows
+    // outside: it has to keep meeting the CTA's per-step barrier below.)
+    const bool row_ok = rA >= 0 && rA < H && strip < P.n_strips;
     const bool store_lane = row_ok && lane >= KB && lane < 32 - KB;
     const int gx0 = (P.chunk0 + (int)blockIdx.y) * P.lx;  // first column this chunk finalises
     const int vx0 = max(gx0, P.c_lo), vx1 = min(gx0 + P.lx, P.c_hi);
@@ -177,6 +179,10 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
                 plain = (plain & ~(1u << m)) | ((pl ? 1u : 0u) << m);
                 pend = nxt;
             }
+            // Keep the CTA's warps in the same unrolled step: the march loop is ~58 KB of straight-line code and the
+            // SM's warps share a 32 KB instruction cache level; warps drifting apart made instruction fetch the
+            // second largest stall (ncu: no_instruction 1.8 cycles per issued instruction at 16384^2).
+            if (P.step_sync) __syncthreads();
         }
     }
 }
@@ -223,6 +229,7 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.apply_gravity = (t == 0 && a.apply_gravity) ? 1 : 0;
     P.omega = a.omega; P.pc = a.pc; P.gdt = a.gdt;
     P.pf = tunables().rb_pf;
+    P.step_sync = tunables().rb_sync;
     // 4 warps (adjacent strips) per CTA: their overlapping rows hit L1; 1 or 2 warps per CTA balance a one-wave launch
     // better but measured 1-5 % slower at 4096^2 and 16384^2
     const int wpc = tunables().rb_wpc == 1 ? 1 : (tunables().rb_wpc == 2 ? 2 : 4);
