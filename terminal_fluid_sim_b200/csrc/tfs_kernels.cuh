@@ -270,8 +270,10 @@ TFS_DEVINL float magic_float(float y, float one) { return __fmaf_rn(y, one, -TFS
 // [cs0, cs1] are clamped for memory safety and reported through *oob (halo too small for this dt).
 // field load: x-slab kernels bypass L1 (ld.global.cg).  Their halo columns are rewritten between launches by another
 // stream (the neighbour's push); with two slabs on ONE device an L1 line from an earlier launch could be stale.
+// (Single GPU: a plain load of a const __restrict__ pointer - the compiler picks the read-only path itself; forcing it
+// with __ldg cost 8 instructions and 2 % in the packed kernel.)
 template <bool SLAB>
-TFS_DEVINL float ldf(const float *p) { return SLAB ? __ldcg(p) : __ldg(p); }
+TFS_DEVINL float ldf(const float *p) { return SLAB ? __ldcg(p) : *p; }
 
 // What an x-slab's advection can reach beyond its own stored columns [cs0, cs1]: the neighbours' memory, read
 // directly over NVLink (the back-trace distance |vel|*dt is unbounded, simulator.rs:211-212, so a halo of
@@ -521,9 +523,9 @@ k_advect32_pair(const float *__restrict__ u, const float *__restrict__ v, const 
                 const __grid_constant__ SlabFar far = SlabFar()) {
     constexpr int RB = 128;  // row distance of the two cells
     const int jA = blockIdx.x * (2 * RB) + threadIdx.x, jB = jA + RB;
-    const int i0 = c_begin + blockIdx.y * CPB;
-    const int c_stop = min(W, c_end);
-    if (L2PF) prefetch_tile_l2(u, v, s, flags, SLAB ? min(W, (int)far.cs1 + 1) : W, H, i0, min(CPB, c_stop - i0), blockIdx.x * (2 * RB), 2 * RB);
+    const int i0 = SLAB ? c_begin + blockIdx.y * CPB : blockIdx.y * CPB;
+    const int c_stop = SLAB ? min(W, c_end) : W;
+    if (L2PF) prefetch_tile_l2(u, v, s, flags, SLAB ? min(W, (int)far.cs1 + 1) : W, H, i0, SLAB ? min(CPB, c_stop - i0) : CPB, blockIdx.x * (2 * RB), 2 * RB);
     // x of every sample in [xlo, xhi): no clamp of simulator.rs:271-288 binds and (SLAB) both sample columns are stored
     const unsigned xlo_bits = SLAB ? __float_as_uint((float)max(1, (int)far.cs0 + 1)) : 0x3f800000u;
     const unsigned xhi_bits = __float_as_uint((float)(SLAB ? min(W - 1, (int)far.cs1) : W - 1));
