@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
         const int li = i - xs0;
         if (row_ok && (unsigned)li < (unsigned)ncols) {  // stored columns lie inside the grid
             const size_t o = (size_t)li * (size_t)H + row_off;
-            r.u = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_u + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_u + o));
-            r.v = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_v + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_v + o));
-            if (!FIRST) r.p = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_p + o)) : __ldg(reinterpret_cast<const float2 *>(P.in_p + o));
+            r.u = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_u + o)) : *reinterpret_cast<const float2 *>(P.in_u + o);
+            r.v = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_v + o)) : *reinterpret_cast<const float2 *>(P.in_v + o);
+            if (!FIRST) r.p = CG ? __ldcg(reinterpret_cast<const float2 *>(P.in_p + o)) : *reinterpret_cast<const float2 *>(P.in_p + o);
             r.f = __ldg(reinterpret_cast<const unsigned short *>(P.flags + o));
             if (FIRST && P.apply_gravity) {
                 if (r.f & TFS_F_LIVE) r.v.x = fadd(r.v.x, P.gdt);
