@@ -183,12 +183,13 @@ def run_ours(args):
     achieved = alg_bytes / (proj_ms / 1e3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of the projection kernel, per launch, from the ncu captures
     # committed under profiles/ (a separate run of the same configuration; never measured inside this timed run)
-    traffic = {"c5": (4.658e11, "profiles/r01_c5_dram_32768_K200.csv"),
-               "c3": (2.30e9, "profiles/r01_systolic4_c3_4096_K100.txt")}.get(args.workload, (None, None))
+    traffic = {("c5", "exact"): (4.708e11, "profiles/r02_c5_exact_dram.csv"),
+               ("c3", "exact"): (2.107e9, "profiles/r02_systolic4_c3.txt"),
+               ("c5", "rb"): (1.454e12, "profiles/r02_c5_rb_dram.csv (29.1 GB per pass x 50 passes)"),
+               ("c3", "rb"): (1.054e10, "profiles/r02_rb_c3.txt (0.42 GB per pass x 25 passes)"),
+               ("c4", "rb"): (9.48e10, "profiles/r02_rb_c4.txt (7.29 GB per pass x 13 passes)")}.get((args.workload, args.mode), (None, None))
     kname = "k_project_systolic4 (gravity + %d-iteration exact projection)" if args.mode == "exact" else \
         "k_project_rb (gravity + %d red-black iterations, 4 per launch; all launches of a step)"
-    if args.mode != "exact":
-        traffic = (None, None)
     roofline = {"kernel": kname % K, "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src, "ms_per_launch": round(proj_ms, 4),
