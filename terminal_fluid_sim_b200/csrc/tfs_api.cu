@@ -585,7 +585,8 @@ int phase_advect(tfs_sim *s, float dt) {
             const tfs::F2K k{two(1.0f), two(-1.0f), two(-0.0f)};
             // 4 columns per block and 64 registers (8 CTAs/SM) are the best of the variants measured on B200 at 4096^2
             // (ms per launch): 8 columns 0.137, 72 / 80 registers 0.123 / 0.130, a rolled march over 8 / 16 / 32 columns
-            // 0.126 / 0.136 / 0.158, an L1 prefetch of the tile 0.123-0.127, against 0.121-0.123 for this form
+            // 0.126 / 0.136 / 0.158, an L1 prefetch of the tile 0.123-0.127, a shared-memory tile kernel (TMA bulk copies, row
+            // pairs, 20 % fewer instructions) 0.125-0.167, against 0.119-0.123 for this form
             constexpr int CPB = 4;
             dim3 grid((unsigned)(H / 256), blocks_for(W, CPB));
             tfs::k_advect32_pair<CPB, 8, true><<<grid, 128, 0, s->stream>>>(s->u, s->v, s->s, s->flags, s->u2, s->v2, s->s2, (int)W,
