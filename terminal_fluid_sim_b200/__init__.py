@@ -6,7 +6,7 @@ from .fluid_sim import (FIELD_FLAGS, FIELD_M, FIELD_P, FIELD_S, FIELD_U, FIELD_V
                         KERNEL_DIAGONAL, KERNEL_SYSTOLIC, MODE_RED_BLACK, MODE_WAVEFRONT_EXACT,
                         FluidSim, PinnedBuffer, SimConfig, SlabGroup, checksum_of_fields, combine_checksums, selftest_division,
                         slab_bounds, PROJ_NONE, PROJ_SYSTOLIC_BLOCK_RING, PROJ_SYSTOLIC_GENERIC, PROJ_DIAGONAL,
-                        PROJ_REDBLACK_FUSED, PROJ_REDBLACK_TWO_LAUNCH)
+                        PROJ_REDBLACK_FUSED, PROJ_REDBLACK_TWO_LAUNCH, PROJ_SMALL_FUSED)
 from ._lib import TfsError  # noqa: F401
 
 __all__ = ["FluidSim", "SimConfig", "PinnedBuffer", "SlabGroup", "TfsError", "selftest_division", "slab_bounds"]

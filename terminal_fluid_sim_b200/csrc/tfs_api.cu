@@ -17,6 +17,7 @@
 #include "tfs_systolic.cuh"
 #include "tfs_systolic4.cuh"
 #include "tfs_redblack.cuh"
+#include "tfs_small.cuh"
 
 #define TFS_VERSION_STRING "tfs-cuda 0.1.0 (sm_100a)"
 
@@ -1100,8 +1101,39 @@ int tfs_upload_blocks(tfs_sim *s, const uint8_t *mask, size_t offset, size_t n) 
 }
 
 namespace {
+// Terminal-sized grids: the whole step in one launch of one CTA, fields in shared memory (tfs_small.cuh).
+bool small_step(const tfs_sim *s) {
+    return !s->slab() && s->opt.kernel == TFS_KERNEL_AUTO && tunables().small_kernel && tfs::small_step_usable((long long)s->W, (long long)s->H);
+}
+int step_small(tfs_sim *s, float dt, cudaEvent_t *ev) {
+    static bool attr_done[64] = {false};
+    if (!attr_done[s->device & 63]) {
+        CU(cudaFuncSetAttribute(tfs::k_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)tfs::small_step_smem(tfs::kSmallMaxCells, 1)));
+        attr_done[s->device & 63] = true;
+    }
+    tfs::SmallParams P{};
+    P.u = s->u; P.v = s->v; P.s = s->s; P.flags = s->flags;
+    P.nu = s->u2; P.nv = s->v2; P.ns = s->s2; P.p = s->p;
+    P.W = (int)s->W; P.H = (int)s->H; P.K = s->opt.iterations; P.redblack = s->opt.mode == TFS_MODE_RED_BLACK;
+    P.omega = s->opt.omega; P.pc = s->cfg.density / dt;  // simulator.rs:155 (inf for dt == 0, like the reference)
+    P.gdt = s->cfg.gravity * dt; P.dt = dt;
+    if (ev) CU(cudaEventRecord(ev[1], s->stream));
+    tfs::k_step_small<<<1, tfs::kSmallThreads, tfs::small_step_smem((long long)s->W, (long long)s->H), s->stream>>>(P);
+    s->launches++;
+    CU(cudaGetLastError());
+    if (ev) { CU(cudaEventRecord(ev[2], s->stream)); CU(cudaEventRecord(ev[3], s->stream)); }
+    std::swap(s->u, s->u2); std::swap(s->v, s->v2); std::swap(s->s, s->s2);  // simulator.rs:240-242
+    std::swap(s->phys[0], s->phys[4]); std::swap(s->phys[1], s->phys[5]); std::swap(s->phys[3], s->phys[7]);
+    s->last_proj = tfs_projection_info{};
+    s->last_proj.kernel = TFS_PROJ_SMALL_FUSED;
+    s->last_proj.passes = 1;
+    return TFS_OK;
+}
+
 int step_body(tfs_sim *s, float dt, cudaEvent_t *ev) {
     int rc;
+    if (small_step(s)) return step_small(s, dt, ev);
     if (s->slab()) {
         rc = check_oob(s, false);  // a finished earlier step whose advection overran: report it now
         if (rc) return rc;

@@ -102,6 +102,7 @@ struct Tunables {
     bool sys_v3 = false;          // TFS_SYS_V3 = 1: generic kernel even when H % 4 == 0
     char sys_order = 0;           // TFS_SYS_ORDER = d / l / h: task order
     int sys_grid = 0;             // TFS_SYS_GRID = n (cap on resident CTAs), -1 = "even"
+    bool small_kernel = true;     // TFS_SMALL = 0: terminal-sized grids take the tiled kernels too
     bool adv_pair = true;         // TFS_ADV_PAIR = 0: one-cell advection kernel
     char advect = 0;              // TFS_ADVECT = vec4 / scalar: generic advection kernels
     int rb_variant = 0;           // TFS_RB_VARIANT = 1: the one-launch-per-colour red-black kernel
@@ -122,6 +123,7 @@ inline const Tunables &tunables() {
         if (const char *e = getenv("TFS_SYS_ORDER")) x.sys_order = e[0];
         if (const char *e = getenv("TFS_SYS_GRID")) x.sys_grid = e[0] == 'e' ? -1 : atoi(e);
         x.adv_pair = geti("TFS_ADV_PAIR", 1) != 0;
+        x.small_kernel = geti("TFS_SMALL", 1) != 0;
         if (const char *e = getenv("TFS_ADVECT")) x.advect = e[0];
         x.rb_variant = geti("TFS_RB_VARIANT", 0);
         x.rb_chunk = geti("TFS_RB_CHUNK", 0);

@@ -144,7 +144,9 @@ __global__ void k_project_redblack(float *__restrict__ u, float *__restrict__ v,
 enum { FT_U = 0, FT_V = 1, FT_S = 2 };
 
 // sample_vector (simulator.rs:269-298).  lx0/ncols translate global columns to storage.
-template <int FT>
+// NC: the field is global memory read through the non-coherent path (__ldg); false = plain loads (the field may then
+// live in shared memory: k_step_small)
+template <int FT, bool NC = true>
 TFS_DEVINL float sample_field(const float *__restrict__ f, float x, float y, const Grid &g, float Wf,
                               float Hf) {
     const float dx = (FT == FT_U) ? 0.0f : 0.5f;   // :277-281
@@ -168,14 +170,15 @@ TFS_DEVINL float sample_field(const float *__restrict__ f, float x, float y, con
     long long cl = xl - g.x0, cr = xr - g.x0;
     cl = cl < 0 ? 0 : (cl > g.ncols - 1 ? g.ncols - 1 : cl);
     cr = cr < 0 ? 0 : (cr > g.ncols - 1 ? g.ncols - 1 : cr);
-    const float f00 = __ldg(f + cl * g.H + yb), f10 = __ldg(f + cr * g.H + yb);
-    const float f11 = __ldg(f + cr * g.H + yt), f01 = __ldg(f + cl * g.H + yt);
+    const float f00 = NC ? __ldg(f + cl * g.H + yb) : f[cl * g.H + yb], f10 = NC ? __ldg(f + cr * g.H + yb) : f[cr * g.H + yb];
+    const float f11 = NC ? __ldg(f + cr * g.H + yt) : f[cr * g.H + yt], f01 = NC ? __ldg(f + cl * g.H + yt) : f[cl * g.H + yt];
     // :294-297, left to right
     return fadd(fadd(fadd(fmul(fmul(sx, sy), f00), fmul(fmul(tx, sy), f10)), fmul(fmul(tx, ty), f11)),
                 fmul(fmul(sx, ty), f01));
 }
 
 // one cell of move_velocity; (lc, j) = storage column / row of an UPDATABLE cell
+template <bool NC = true>
 TFS_DEVINL void advect_cell(const float *__restrict__ u, const float *__restrict__ v,
                             const float *__restrict__ s, const Grid &g, long long lc, long long j,
                             float dt, float Wf, float Hf, float uC, float vC, float &nu, float &nv,
@@ -184,23 +187,23 @@ TFS_DEVINL void advect_cell(const float *__restrict__ u, const float *__restrict
     const long long idx = lc * H + j;
     const float fi = (float)(g.x0 + lc), fj = (float)j;
     // u component (:207-213), avg_vertical (:245-255): ((((0+a)+b)+c)+d)*0.25
-    const float vL = __ldg(v + idx - H), vLT = __ldg(v + idx - H + 1), vT = __ldg(v + idx + 1);
+    const float vL = NC ? __ldg(v + idx - H) : v[idx - H], vLT = NC ? __ldg(v + idx - H + 1) : v[idx - H + 1], vT = NC ? __ldg(v + idx + 1) : v[idx + 1];
     const float avg_v = fmul(fadd(fadd(fadd(fadd(0.0f, vL), vLT), vT), vC), 0.25f);
     float xp = fsub(fi, fmul(uC, dt));
     float yp = fsub(fadd(fj, 0.5f), fmul(avg_v, dt));
-    nu = sample_field<FT_U>(u, xp, yp, g, Wf, Hf);
+    nu = sample_field<FT_U, NC>(u, xp, yp, g, Wf, Hf);
     // v component (:216-224), avg_horizontal (:257-267)
-    const float uB = __ldg(u + idx - 1), uRB = __ldg(u + idx + H - 1), uR = __ldg(u + idx + H);
+    const float uB = NC ? __ldg(u + idx - 1) : u[idx - 1], uRB = NC ? __ldg(u + idx + H - 1) : u[idx + H - 1], uR = NC ? __ldg(u + idx + H) : u[idx + H];
     const float avg_u = fmul(fadd(fadd(fadd(fadd(0.0f, uB), uRB), uR), uC), 0.25f);
     xp = fsub(fadd(fi, 0.5f), fmul(avg_u, dt));
     yp = fsub(fj, fmul(vC, dt));
-    nv = sample_field<FT_V>(v, xp, yp, g, Wf, Hf);
+    nv = sample_field<FT_V, NC>(v, xp, yp, g, Wf, Hf);
     // smoke (:227-237); the guard at :227 is always true for an updatable cell
     const float cv = fmul(fadd(vC, vT), 0.5f);
     const float cu = fmul(fadd(uC, uR), 0.5f);
     xp = fsub(fadd(fi, 0.5f), fmul(cu, dt));
     yp = fsub(fadd(fj, 0.5f), fmul(cv, dt));
-    ns = sample_field<FT_S>(s, xp, yp, g, Wf, Hf);
+    ns = sample_field<FT_S, NC>(s, xp, yp, g, Wf, Hf);
 }
 
 // VEC = 4: one thread per 4 consecutive rows of a column, 128-bit loads/stores (H % 4 == 0);

@@ -21,7 +21,7 @@ MODE_WAVEFRONT_EXACT, MODE_RED_BLACK = 0, 1
 KERNEL_AUTO, KERNEL_SYSTOLIC, KERNEL_DIAGONAL = 0, 1, 2
 FIELD_U, FIELD_V, FIELD_P, FIELD_S, FIELD_M, FIELD_FLAGS = range(6)
 (PROJ_NONE, PROJ_SYSTOLIC_BLOCK_RING, PROJ_SYSTOLIC_GENERIC, PROJ_DIAGONAL, PROJ_REDBLACK_FUSED,
- PROJ_REDBLACK_TWO_LAUNCH) = range(6)
+ PROJ_REDBLACK_TWO_LAUNCH, PROJ_SMALL_FUSED) = range(7)
 
 
 @dataclass

@@ -99,8 +99,9 @@ def test_block_ring_kernel_equals_diagonal_kernel_on_device_at_8192():
 
 def test_auto_kernel_is_the_block_ring_kernel_for_every_iteration_count():
     """No silent fallback to the generic kernel: with H % 4 == 0 KERNEL_AUTO runs k_project_systolic4 for K = 1..64
-    (and every one of them is bit-identical to the oracle)."""
-    W, H = 96, 64
+    (and every one of them is bit-identical to the oracle).  224 x 64 = 14336 cells: above the 12800 cells that
+    KERNEL_AUTO gives to the one-CTA kernel."""
+    W, H = 224, 64
     for K in range(1, 65):
         g = tfs.FluidSim(W, H, tfs.SimConfig(gravity=-3.0), iterations=K)
         o = OracleSim(W, H, gravity=-3.0, iterations=K)
@@ -111,7 +112,7 @@ def test_auto_kernel_is_the_block_ring_kernel_for_every_iteration_count():
         assert info["passes"] * info["kg"] * info["nw"] >= K
         assert_same(g, o, f"K={K} shape {info}")
         g.close()
-    g = tfs.FluidSim(W, 63, iterations=10)                    # H % 4 != 0: the generic kernel, and it says so
+    g = tfs.FluidSim(W, 63, iterations=10)                    # H % 4 != 0: the generic kernel, and it says so (14112 cells)
     g.next_step(DT)
     assert g.last_projection()["kernel"] == tfs.PROJ_SYSTOLIC_GENERIC
 
@@ -119,7 +120,7 @@ def test_auto_kernel_is_the_block_ring_kernel_for_every_iteration_count():
 def test_workspace_survives_resize_to_smaller_grid_and_iteration_change():
     """progress counters of the block-ring kernel must not be read from stale records when the
     workspace is reused with another layout (smaller grid, other shape, generic kernel first)."""
-    g = tfs.FluidSim(128, 64, tfs.SimConfig(gravity=2.0), iterations=50)
+    g = tfs.FluidSim(128, 64, tfs.SimConfig(gravity=2.0), iterations=50, kernel=tfs.KERNEL_SYSTOLIC)   # not the one-CTA kernel
     o = OracleSim(128, 64, gravity=2.0, iterations=50)
     for sim in (g, o):
         sim.fill_random_velocity(3, 80.0)
@@ -177,7 +178,8 @@ def test_redblack_fused_bit_exact_vs_its_cpu_statement(W, H, K, grav, frac):
     g.fill_random_velocity(21, 40.0); o.fill_random_velocity(21, 40.0)
     for st in range(3):
         g.next_step(DT); o.step(DT)
-        assert g.last_projection()["kernel"] == tfs.PROJ_REDBLACK_FUSED
+        want = tfs.PROJ_SMALL_FUSED if W * H <= 12800 else tfs.PROJ_REDBLACK_FUSED
+        assert g.last_projection()["kernel"] == want
         assert_same(g, o, f"red-black {W}x{H} K={K} step {st}")
     g.phase_gravity(DT); o.add_gravity(DT)                    # the phases on their own (gravity not fused)
     g.phase_project(DT); o.make_incompressible(DT)
@@ -185,9 +187,9 @@ def test_redblack_fused_bit_exact_vs_its_cpu_statement(W, H, K, grav, frac):
 
 
 def test_redblack_odd_height_takes_the_simple_kernel_and_is_exact_too():
-    g = tfs.FluidSim(90, 37, iterations=11, mode=tfs.MODE_RED_BLACK)
-    o = OracleSim(90, 37, iterations=11, mode=1)
-    g.scene_disc(30, 18, 6); o.scene_disc(30, 18, 6)
+    g = tfs.FluidSim(190, 97, iterations=11, mode=tfs.MODE_RED_BLACK)
+    o = OracleSim(190, 97, iterations=11, mode=1)
+    g.scene_disc(30, 48, 9); o.scene_disc(30, 48, 9)
     for st in range(2):
         g.next_step(DT); o.step(DT)
         assert g.last_projection()["kernel"] == tfs.PROJ_REDBLACK_TWO_LAUNCH
@@ -337,3 +339,49 @@ def test_smoke_pipe_and_wind_column_known_answers_on_device():
         assert np.array_equal(g.get_smoke_grid().reshape(5, H), want), (H, size)
         u = g.u.reshape(5, H)
         assert np.all(u[1] == np.float32(12.5)) and np.count_nonzero(u) == H
+
+
+# ---- terminal-sized grids: the whole step in one CTA (k_step_small) ------------------------------------------------
+SMALL_CASES = ["bench_100x100", "term_80x48_disc", "term_48x42_random_gravity", "adversarial_64x40", "odd_37x23", "default_2x2",
+               "thin_3x64"]
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_small_grid_kernel_reproduces_goldens(name):
+    """KERNEL_AUTO on the reference's own sizes (cargo bench 100 x 100, the terminal-derived 80 x 48 and 48 x 42): one launch
+    per step, bit-identical to the goldens and to the oracle after every step"""
+    from tests.helpers import load_golden, sim_kwargs
+    z, prm = load_golden(name)
+    kw = sim_kwargs(prm)
+    g = tfs.FluidSim(prm["W"], prm["H"], tfs.SimConfig(kw["gravity"], kw["wind_speed"], kw["smoke_size"], kw["density"]),
+                     iterations=kw["iterations"], omega=kw["omega"])
+    o = OracleSim(prm["W"], prm["H"], kw["gravity"], kw["wind_speed"], kw["smoke_size"], kw["density"], iterations=kw["iterations"],
+                  omega=kw["omega"])
+    g.write_field(tfs.FIELD_M, z["mask"]); o.m[:] = z["mask"]
+    for f, fid in (("u", tfs.FIELD_U), ("v", tfs.FIELD_V), ("s", tfs.FIELD_S)):
+        g.write_field(fid, z[f + "0"]); getattr(o, f)[:] = z[f + "0"]
+    launches = g.launch_count()
+    for st in range(1, prm["steps"] + 1):
+        g.next_step(prm["dt"]); o.step(prm["dt"])
+        assert g.last_projection()["kernel"] == tfs.PROJ_SMALL_FUSED
+        assert_same(g, o, f"{name} step {st}")
+        if st in prm["keep"]:
+            for f in "uvps":
+                assert bits_equal(getattr(g, f), z[f"{f}_step{st}"]), f"{name} golden {f} step {st}"
+    assert g.launch_count() - launches <= prm["steps"] + 1      # one launch per step (+ the flag refresh after the mask upload)
+
+
+@pytest.mark.parametrize("W,H,K,mode", [(113, 113, 7, 0), (113, 113, 7, 1), (100, 100, 50, 1), (64, 200, 0, 0), (9, 1400, 3, 0),
+                                        (1400, 9, 3, 1), (5, 5, 4, 0)])
+def test_small_grid_kernel_edge_sizes_and_modes(W, H, K, mode):
+    g = tfs.FluidSim(W, H, tfs.SimConfig(gravity=-4.0), iterations=K, mode=mode)
+    o = OracleSim(W, H, gravity=-4.0, iterations=K, mode=mode)
+    g.scene_random(3, frac_to_threshold(0.1)); o.scene_random(3, 0.1)
+    g.fill_random_velocity(8, 90.0); o.fill_random_velocity(8, 90.0)
+    for st in range(3):
+        g.next_step(DT); o.step(DT)
+        assert g.last_projection()["kernel"] == tfs.PROJ_SMALL_FUSED
+        assert_same(g, o, f"{W}x{H} K={K} mode {mode} step {st}")
+    big = tfs.FluidSim(114, 113, iterations=4)                  # 12882 cells: just above the limit
+    big.next_step(DT)
+    assert big.last_projection()["kernel"] != tfs.PROJ_SMALL_FUSED
