@@ -54,7 +54,7 @@ typedef enum tfs_mode { TFS_MODE_WAVEFRONT_EXACT = 0, TFS_MODE_RED_BLACK = 1 } t
 
 /* Which kernel implements the projection (results do not depend on it within one mode). */
 typedef enum tfs_kernel {
-    TFS_KERNEL_AUTO = 0,     /* <= 12800 cells: one-CTA shared-memory step; else systolic (exact) / fused (red-black) */
+    TFS_KERNEL_AUTO = 0,     /* terminal-sized grids (<= 8192 cells exact, <= 12800 red-black): one-CTA shared-memory step; else systolic (exact) / fused (red-black) */
     TFS_KERNEL_SYSTOLIC = 1, /* register-resident systolic wavefront, temporally blocked */
     TFS_KERNEL_DIAGONAL = 2  /* one launch per anti-diagonal wavefront (simple, slow) */
 } tfs_kernel;
@@ -172,7 +172,7 @@ typedef enum tfs_projection_kernel {
     TFS_PROJ_DIAGONAL = 3,            /* k_project_wavefront: one launch per anti-diagonal */
     TFS_PROJ_REDBLACK_FUSED = 4,      /* k_project_rb: temporally blocked red-black (even height) */
     TFS_PROJ_REDBLACK_TWO_LAUNCH = 5, /* k_project_redblack: one launch per colour */
-    TFS_PROJ_SMALL_FUSED = 6          /* k_step_small: the whole step of a terminal-sized grid in one CTA (KERNEL_AUTO, <= 12800 cells) */
+    TFS_PROJ_SMALL_FUSED = 6          /* k_step_small: the whole step of a terminal-sized grid in one CTA (KERNEL_AUTO) */
 } tfs_projection_kernel;
 typedef struct tfs_projection_info {
     int32_t kernel; /* tfs_projection_kernel */

@@ -1102,8 +1102,13 @@ int tfs_upload_blocks(tfs_sim *s, const uint8_t *mask, size_t offset, size_t n) 
 
 namespace {
 // Terminal-sized grids: the whole step in one launch of one CTA, fields in shared memory (tfs_small.cuh).
+// Measured on B200 (ms per step, one-CTA kernel vs tiled kernels): 48 x 42: 0.21 vs 0.35 exact, 0.17 vs 0.49 red-black;
+// 80 x 48: 0.27 vs 0.36, 0.21 vs 0.49; 100 x 100: 0.38 vs 0.36, 0.31 vs 0.45 - one SM stops paying off for the exact
+// order at about 8000 cells (its wavefront needs W + H + 2K barriers), for red-black only where shared memory ends.
 bool small_step(const tfs_sim *s) {
-    return !s->slab() && s->opt.kernel == TFS_KERNEL_AUTO && tunables().small_kernel && tfs::small_step_usable((long long)s->W, (long long)s->H);
+    const long long cells = (long long)s->W * (long long)s->H;
+    return !s->slab() && s->opt.kernel == TFS_KERNEL_AUTO && tunables().small_kernel && tfs::small_step_usable((long long)s->W, (long long)s->H) &&
+           (s->opt.mode == TFS_MODE_RED_BLACK || cells <= tfs::kSmallMaxCellsExact);
 }
 int step_small(tfs_sim *s, float dt, cudaEvent_t *ev) {
     static bool attr_done[64] = {false};

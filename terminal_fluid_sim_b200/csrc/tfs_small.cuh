@@ -22,6 +22,7 @@ namespace tfs {
 
 constexpr int kSmallThreads = 1024;
 constexpr long long kSmallMaxCells = 12800;  // 17 B per cell of dynamic shared memory: 217.6 KB of the 227 KB a CTA may use
+constexpr long long kSmallMaxCellsExact = 8192;  // exact order: above this the systolic kernel on several SMs is as fast
 
 struct SmallParams {
     const float *u, *v, *s;      // fields before the step
