@@ -1,5 +1,5 @@
 """Timing tool (one GPU): per-step and per-phase device time of one or more configurations, each in its own process
-so that the library's read-once tuning knobs (DESIGN.md section 3.6) can differ between them.
+so that the library's read-once tuning knobs (DESIGN.md section 3.7) can differ between them.
 
     python scripts/timing.py c3                      # BASELINE config by name (c1 .. c5), exact mode
     python scripts/timing.py c3:rb c4:rb c5          # several; ':rb' = red-black mode

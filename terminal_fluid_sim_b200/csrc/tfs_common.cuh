@@ -92,7 +92,7 @@ __host__ TFS_DEVINL uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// Tuning / debugging knobs (DESIGN.md section 3.6).  They are environment variables because none is part of
+// Tuning / debugging knobs (DESIGN.md section 3.7).  They are environment variables because none is part of
 // the product's interface; they are read ONCE per process, on the first call that needs them (tfs_create),
 // never on the step path.
 struct Tunables {
