@@ -185,11 +185,11 @@ def run_ours(args):
     # committed under profiles/ (a separate run of the same configuration; never measured inside this timed run)
     traffic = {("c5", "exact"): (4.708e11, "profiles/r02_c5_exact_dram.csv"),
                ("c3", "exact"): (2.107e9, "profiles/r02_systolic4_c3.txt"),
-               ("c5", "rb"): (1.454e12, "profiles/r02_c5_rb_dram.csv (29.1 GB per pass x 50 passes)"),
-               ("c3", "rb"): (1.054e10, "profiles/r02_rb_c3.txt (0.42 GB per pass x 25 passes)"),
-               ("c4", "rb"): (9.48e10, "profiles/r02_rb_c4.txt (7.29 GB per pass x 13 passes)")}.get((args.workload, args.mode), (None, None))
+               ("c5", "rb"): (1.922e12, "profiles/r02b_c5_rb_dram.csv (28.7 GB per pass x 67 passes)"),
+               ("c3", "rb"): (1.438e10, "profiles/r02b_rb_c3.txt (0.423 GB per pass x 34 passes)"),
+               ("c4", "rb"): (1.231e11, "profiles/r02b_rb_c4.txt (7.24 GB per pass x 17 passes)")}.get((args.workload, args.mode), (None, None))
     kname = "k_project_systolic4 (gravity + %d-iteration exact projection)" if args.mode == "exact" else \
-        "k_project_rb (gravity + %d red-black iterations, 4 per launch; all launches of a step)"
+        "k_project_rb (gravity + %d red-black iterations, 3 per launch; all launches of a step)"
     roofline = {"kernel": kname % K, "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src, "ms_per_launch": round(proj_ms, 4),

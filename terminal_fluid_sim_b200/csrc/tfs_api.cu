@@ -117,11 +117,12 @@ struct tfs_sim {
 namespace {
 
 // Halo columns stored on each side of a slab.  Advection reaches ceil(max|vel|*dt) + 2 columns.  The temporally blocked
-// red-black pass (tfs_redblack.cuh, NS = 8 stages) needs NS + 1 on the LEFT: the first stored column carries a wrong
+// red-black pass (tfs_redblack.cuh, NS = 2 * kRbKB stages, at most 8) needs NS + 1 on the LEFT: the first stored column carries a wrong
 // flag byte (its left neighbour's mask is not stored), so it is wrong from stage 0, the column d to its right from
 // stage d - and the first OWNED column's stored u is also the right face of the column before it, which therefore
 // has to be exact through the last stage.  10 keeps the column pitch of the pushes even.
 constexpr long long kHalo = 10;
+static_assert(2 * tfs::kRbKB + 1 <= kHalo, "the slab halo must cover the red-black pass's overlap");
 constexpr int kSlabMaxPasses = 64;    // passes a slab workspace is sized for
 constexpr unsigned kBlobMagic = 0x54465331u;  // "TFS1"
 

@@ -25,11 +25,16 @@
 //     same kernel serves x-slabs (the slab's stored halo columns are the chunk overlap; the slab keeps NS + 2 of
 //     them because its outermost stored column has a wrong flag byte, see kHalo in tfs_api.cu).
 //   * warp-uniform fast update when every cell of a column's 64 rows is plain interior fluid (11 flops/cell).
-//     Measured and rejected (same B200, 4096^2 K=100 / 32768^2 2 % obstacles K=200, ms per projection): a straight-
-//     line step for an all-plain window 4.73 / 745 and an instantiation without the per-stage "stage active" test
-//     4.85 / 684 against 4.63 / 660 for this form; the general update out of line (__noinline__) 6.9 / 948.  The
-//     unrolled march loop is ~64 KB of code for 20 unsynchronised warps per SM: instruction fetch, not arithmetic,
-//     decides between these variants.
+//
+// KB = 3 (kRbKB): 6 window columns, 52 exact rows per strip, 80 registers -> 6 CTAs (24 warps) per SM and 36 KB of
+// unrolled march loop.  Measured on one B200, ms per projection at 1024^2 K=40 / 4096^2 K=100 / 16384^2 K=50 /
+// 32768^2 K=200: KB = 4 (8 columns, 48 rows, 96 registers, 5 CTAs, 57 KB of loop) 0.374 / 4.55 / 28.5 / 571;
+// KB = 3: 0.343 / 4.17 / 23.7 / 495; KB = 2 (64 registers, 8 CTAs, twice the passes) 0.332 / 5.47 / 31.2 / 491;
+// KB = 3 squeezed to 72 registers for 7 CTAs 0.370 / 4.66 / 25.6 / 522.  The kernel is bound by dependent-issue
+// latency and instruction fetch, not by HBM: more resident warps and a smaller loop win over fewer passes.
+// Measured and rejected at KB = 4 (4096^2 K=100 / 32768^2 2 % obstacles K=200): a straight-line step for an all-plain
+// window 4.73 / 745, an instantiation without the per-stage "stage active" test 4.85 / 684 against 4.63 / 660; the
+// general update out of line (__noinline__) 6.9 / 948.
 #pragma once
 #include "tfs_systolic.cuh"  // cell_update4
 
@@ -55,7 +60,7 @@ struct RbParams {
 // ANOTHER stream (the neighbour's push): a line kept in L1 from an earlier launch would be stale when two slabs share one
 // device.  A single-GPU handle reads through L1 (ld.global.nc), where the rows shared by adjacent strips hit.
 template <int KB, bool FIRST, bool CG>
-__global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
+__global__ void __launch_bounds__(128, KB <= 2 ? 8 : (KB <= 3 ? 6 : 5)) k_project_rb(RbParams P) {
     constexpr int NS = 2 * KB;       // stages per pass = columns in the register window = overlap
     constexpr int V = 64 - 2 * NS;   // rows of a strip that are exact after NS stages
     static_assert(V >= 8, "too many fused iterations for a 64-row strip");
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(128, 5) k_project_rb(RbParams P) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-constexpr int kRbKB = 4;  // iterations fused per pass: 8 window columns, 48 exact rows per 64-row strip
+constexpr int kRbKB = 3;  // iterations fused per pass: 6 window columns, 52 exact rows per 64-row strip
 
 struct RbLaunchArgs {
     float *set[2][3];      // [set][u, v, p]; pass t reads set t & 1 and writes the other
@@ -215,13 +220,13 @@ inline cudaError_t redblack_pass(const RbLaunchArgs &a, int t, int k_act, cudaSt
     P.W = (int)a.W; P.H = (int)a.H; P.xs0 = (int)a.xs0; P.ncols = (int)a.ncols; P.c_lo = (int)a.c_lo; P.c_hi = (int)a.c_hi;
     P.n_strips = (int)((a.H + V - 1) / V);
     // Chunk length: every warp marches lx + 2*NS columns to finalise lx of them, so long chunks waste less, but a grid
-    // that yields fewer warps than the GPU holds (148 SMs x 20) runs them at single-warp latency: take the shortest
-    // chunk that still fits in one wave, 128 columns at most.
-    int lx = 128;
+    // that yields fewer warps than the GPU holds (148 SMs x 24 at KB = 3) runs them at single-warp latency: take the
+    // shortest chunk that still fits in one wave, 126 columns (the multiple of NS below 128) at most.
+    int lx = 128 / NS * NS;
     if (a.chunk_len > 0) lx = (a.chunk_len + NS - 1) / NS * NS;
     else
         for (int c = 2 * NS; c < 128; c *= 2)
-            if ((long long)P.n_strips * ((a.c_hi - a.c_lo + c - 1) / c) <= 148LL * 20) { lx = c; break; }
+            if ((long long)P.n_strips * ((a.c_hi - a.c_lo + c - 1) / c) <= 148LL * 4 * (KB <= 2 ? 8 : (KB <= 3 ? 6 : 5))) { lx = c; break; }
     P.lx = lx;
     P.chunk0 = (int)(a.c_lo / P.lx);
     const int n_chunks = (int)((a.c_hi + P.lx - 1) / P.lx) - P.chunk0;
