@@ -106,7 +106,7 @@ struct Sys4Smem {
     float out_u[32][ROUT];
     float out_v[32][ROUT];
     float out_p[32][ROUT];
-    float4 grp[2][NW][32];
+    float4 grp[2][NW + 1][32];  // slot 0: the feeder warp's k = 0 operands; slot g + 1: hand-over of k-group g
     float4 rec[NR][NW][G][KG];
     unsigned char in_f[32][RIN + 4];  // +4: odd word pitch, fewer bank conflicts on the diagonal byte reads
     unsigned long long in_full[NS_IN], in_empty[NS_IN];
@@ -117,7 +117,7 @@ struct Sys4Smem {
 };
 
 template <int KG, int NW, int G, int RB>
-__global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
+__global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
     using SM = Sys4Smem<KG, NW, G, RB>;
     static_assert(RB == 16 || RB == 32, "ring blocks are 16 or 32 rows");
     static_assert(RB % G == 0, "a ring block is a whole number of record intervals");
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
 
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const bool is_loader = g == NW, is_storer = g == NW + 1;
+    const bool is_loader = g == NW, is_storer = g == NW + 1, is_feeder = g == NW + 2;
     const long long W = P.W, H = P.H;
     const int n_tasks = P4.n_tasks;
     const Sys4Slab &SL = P4.slab;
@@ -379,60 +379,28 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                 for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long *)&P.trace[((NW + 1) * 8 + i)], (unsigned long long)tr_acc[i]);
             }
 #endif
-        } else {
-            // ================================== compute warps =========================================
+        } else if (is_feeder) {
+            // ===================================== FEEDER ===========================================
+            // The k = 0 operands of the first k-group, delivered in the k-groups' own hand-over format (slot 0 of
+            // grp) so that all compute warps run the same code: with the ring reads, bounds tests and the gravity
+            // add in its step, the first compute warp executed 178 instructions per step against 128 of the others,
+            // which waited for it at the step barrier 17 % of their time (ncu source page, round 2).  Iteration tf
+            // runs alongside compute step tf and delivers u, v of step tf + 1 and p, flags of step tf + 2 (the
+            // two-step path of the compute loop); iterations -2 and -1 prime the first k-group.
+            // Operands of step tau: u[q+1, rho], p[q, rho], flags[q, rho], v[q, rho+1], flags[q, rho+1] with
+            // rho = tau - lane - 1.
             const bool grav = first_pass && P.apply_gravity;
             const long long q = q0 + lane;
-            // records go to slot lb + 1, or straight into slot 0 of the right rank for the last local band
-            float4 *rec_out = (last_local && SL.rec_peerR[par])
-                                  ? SL.rec_peerR[par] + (size_t)g * rec_stride
-                                  : P.bnd + (((size_t)par * (SL.nb_local + 1) + lb + 1) * NW + g) * rec_stride;
             const bool col_ok = q >= 0 && q < W;
             const bool colp_ok = q + 1 >= 0 && q + 1 < W;
-
-            float uL[KG], uRo[KG], vB[KG], vTo[KG], pin[KG], pd[KG];
-#pragma unroll
-            for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
-            unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
-
-            // k = 0 operands of step tau: u[q+1, rho], p[q, rho], flags[q, rho], v[q, rho+1], flags[q, rho+1]
-            // with rho = tau - lane - 1, read from the row rings (k-group 0 only).  rr / rr1 are this
-            // lane's ring positions of rho / rho + 1 and advance by one per step.
-            constexpr int RIN = SM::RIN, ROUT = SM::ROUT;
+            constexpr int RIN = SM::RIN;
             const int Hi = (int)H;
-            int rr = ((-lane - 1) % RIN + RIN) % RIN;      // rho at tau = 0
+            int rr = ((-2 - lane) % RIN + RIN) % RIN;  // ring position of row tf - lane at tf = -2
             int rr1 = (rr + 1 == RIN) ? 0 : rr + 1;
-            struct K0 { float su, sv, sp; unsigned f0, f1; };
-            auto load_k0 = [&]() -> K0 {  // operands of the step whose rho sits at rr
-                K0 o;
-                o.su = sm.in_u[lane][rr];
-                o.sp = sm.in_p[lane][rr];
-                o.f0 = sm.in_f[lane][rr];
-                o.sv = sm.in_v[lane][rr1];
-                o.f1 = sm.in_f[lane][rr1];
-                return o;
-            };
-            auto advance_ring = [&]() {
-                rr = rr1;
-                rr1 = (rr1 + 1 == RIN) ? 0 : rr1 + 1;
-            };
-            auto apply_k0 = [&](int tau, const K0 &o) {
-                const int row = tau - lane - 1;
-                const bool row_ok = (unsigned)row < (unsigned)Hi;
-                const bool rowp_ok = (unsigned)(row + 1) < (unsigned)Hi;
-                const unsigned f0 = (col_ok && row_ok) ? o.f0 : 0u;
-                const unsigned f1 = (col_ok && rowp_ok) ? o.f1 : 0u;
-                uRo[0] = (colp_ok && row_ok) ? o.su : 0.0f;
-                float vv = (col_ok && rowp_ok) ? o.sv : 0.0f;
-                if (grav && (f1 & TFS_F_LIVE)) vv = fadd(vv, P.gdt);  // simulator.rs:147
-                vTo[0] = vv;
-                pin[0] = (!first_pass && col_ok && row_ok) ? o.sp : 0.0f;
-                fl = (fl & ~0xFu) | (f0 & 15u);
-            };
-            // input blocks: block n is first touched (by lane 0, row rho+1 = RB*n) when preparing step RB*n;
-            // rows in use are [tau-32, tau], so block n-(NS_IN-1) is then behind lane 31 and goes back to the loader
+            // input blocks: block n is first touched (by lane 0, row RB*n) in iteration RB*n - 1; rows in use are
+            // [tf-31, tf+1], so block n-(NS_IN-1) is then behind lane 31 and goes back to the loader
             int in_slot = 0, in_par = 0, in_n = 0;         // next block to acquire
-            int rel_slot = 0;                              // slot of block in_n - 2
+            int rel_slot = 0;                              // slot of block in_n - (NS_IN - 1)
             auto acquire_in_block = [&]() {
                 mbar_wait(&sm.in_full[in_slot], in_par);
                 if (in_n >= NS_IN - 1) {
@@ -443,6 +411,42 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                 ++in_n;
                 if (++in_slot == NS_IN) { in_slot = 0; in_par ^= 1; }
             };
+            acquire_in_block();
+            for (int tf = -2; tf < T; ++tf) {
+                if (tf + 1 < T) {
+                    if (tf + 1 > 0 && ((tf + 1) % RB) == 0) acquire_in_block();
+                    const int row = tf - lane;  // rho of step tf + 1; rho of step tf + 2 is row + 1
+                    const bool row_ok = (unsigned)row < (unsigned)Hi;
+                    const bool rowp_ok = (unsigned)(row + 1) < (unsigned)Hi;
+                    const float su = sm.in_u[lane][rr];
+                    const float sv = sm.in_v[lane][rr1];
+                    const float sp = sm.in_p[lane][rr1];
+                    const unsigned f1 = (col_ok && rowp_ok) ? (unsigned)sm.in_f[lane][rr1] : 0u;
+                    float vv = (col_ok && rowp_ok) ? sv : 0.0f;
+                    if (grav && (f1 & TFS_F_LIVE)) vv = fadd(vv, P.gdt);  // simulator.rs:147
+                    float4 o;
+                    o.x = (colp_ok && row_ok) ? su : 0.0f;
+                    o.y = vv;
+                    o.z = (!first_pass && col_ok && rowp_ok) ? sp : 0.0f;
+                    o.w = __uint_as_float(f1 & 15u);
+                    sm.grp[tf & 1][0][lane] = o;
+                    rr = rr1;
+                    rr1 = (rr1 + 1 == RIN) ? 0 : rr1 + 1;
+                }
+                bar_sync_imm<BAR_STEP, NCT + 32>();
+            }
+        } else {
+            // ================================== compute warps =========================================
+            // records go to slot lb + 1, or straight into slot 0 of the right rank for the last local band
+            float4 *rec_out = (last_local && SL.rec_peerR[par])
+                                  ? SL.rec_peerR[par] + (size_t)g * rec_stride
+                                  : P.bnd + (((size_t)par * (SL.nb_local + 1) + lb + 1) * NW + g) * rec_stride;
+
+            float uL[KG], uRo[KG], vB[KG], vTo[KG], pin[KG], pd[KG];
+#pragma unroll
+            for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
+            unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
+            constexpr int ROUT = SM::ROUT;
             constexpr unsigned FULL = (KG == 8) ? 0xFFFFFFFFu : ((1u << (4 * KG)) - 1u);
             const bool group_active = (g + 1) * KG <= k_act;  // every iteration of this k-group runs in this pass
             // record-interval bookkeeping (all k-groups) and output-ring bookkeeping (last k-group)
@@ -454,10 +458,19 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
             const float4 *rec_base = &sm.rec[0][g][0][0];
             constexpr int REC_SLOT_STRIDE = NW * G * KG;    // float4 per ring slot
 
-            if (g == 0) {
-                acquire_in_block();
-                apply_k0(0, load_k0());
-                advance_ring();
+            // two priming rounds for the first k-group: p, flags of step 0, then u, v of step 0 and p, flags of step 1
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                bar_sync_imm<BAR_STEP, NCT + 32>();
+                if (g == 0) {
+                    const float4 gi = sm.grp[pr][0][lane];
+                    uRo[0] = gi.x;
+                    vTo[0] = gi.y;
+                    pin[0] = pd[0];
+                    pd[0] = gi.z;
+                    fld |= __float_as_uint(gi.w);
+                    if (pr == 0) { fl = fld; fld = 0u; }
+                }
             }
             TFS_TR_DECL
             for (int t = 0, sg = 0; t < T; ++t) {
@@ -476,19 +489,12 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                     }
                 }
                 TFS_TR(6)
-                // ---- early loads: left band's record (for lane 0) and next step's k = 0 operands
+                // ---- early loads: left band's record (for lane 0)
                 float4 lr[KG];
                 {
                     const float4 *rp = rec_base + rec_slot * REC_SLOT_STRIDE + sg * KG;
 #pragma unroll
                     for (int kk = 0; kk < KG; ++kk) lr[kk] = rp[kk];  // broadcast read
-                }
-                const bool have_next = (g == 0) && (t + 1 < T);
-                K0 nk0 = {0.f, 0.f, 0.f, 0u, 0u};
-                if (have_next) {
-                    if (((t + 1) % RB) == 0) acquire_in_block();
-                    nk0 = load_k0();
-                    advance_ring();
                 }
                 TFS_TR(1)
                 // ---- KG independent cell updates ---------------------------------------------------
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                 s_flv = (lane == 0) ? __float_as_uint(lr[0].w) : s_flv;
                 TFS_TR(3)
                 // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
-                sm.grp[t & 1][g][lane] =
+                sm.grp[t & 1][g + 1][lane] =
                     make_float4(a[KG - 1], s_v[KG - 1], s_p[KG - 1], __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
                 if (g == NW - 1) {  // iteration KB-1 retired: final values of cell (q-(KB-1), t-lane-KB) -> output ring
                     if (t - lane - KB >= 0) {
@@ -588,17 +594,15 @@ __global__ void __launch_bounds__(32 * (NW + 2), (RB == 16 && NW <= 4 && KG <= 5
                     ++sg;
                 }
                 TFS_TR(4)
-                bar_sync_imm<BAR_STEP, NCT>();
+                bar_sync_imm<BAR_STEP, NCT + 32>();
                 TFS_TR(5)
-                if (g > 0) {
-                    const float4 gi = sm.grp[t & 1][g - 1][lane];
+                {  // from the previous k-group, or from the feeder warp (g == 0)
+                    const float4 gi = sm.grp[t & 1][g][lane];
                     uRo[0] = gi.x;
                     vTo[0] = gi.y;
                     pin[0] = pd[0];
                     pd[0] = gi.z;
                     fld |= __float_as_uint(gi.w);  // the nibble for slot 0, two steps from now
-                } else if (have_next) {
-                    apply_k0(t + 1, nk0);
                 }
             }
 #ifdef TFS_SYS_TRACE
@@ -801,7 +805,7 @@ struct Sys4Launch {
                 *msg = "cudaFuncSetAttribute(max dynamic smem)";
                 return e;
             }
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 2), smem)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 3), smem)) != cudaSuccess) return e;
             attr_set[di] = true;
         }
         const int occ = occ_dev[di];
@@ -831,7 +835,7 @@ struct Sys4Launch {
         cudaMemsetAsync(d_tt[di], 0, (size_t)n_tasks * 4 * sizeof(unsigned long long), a.stream);
         P4.ttrace = d_tt[di];
 #endif
-        kern<<<grid, 32 * (NW + 2), smem, a.stream>>>(P4);
+        kern<<<grid, 32 * (NW + 3), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
         ws4.last_kg = KG; ws4.last_nw = NW; ws4.last_passes = P.n_passes;
