@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
             sm.task = atomicAdd(P.ticket, 1);
             for (int i = 0; i < NS_IN; ++i) { mbar_init(&sm.in_full[i], 32); mbar_init(&sm.in_empty[i], 1); }
             for (int i = 0; i < NR; ++i) { mbar_init(&sm.rec_full[i], 32); mbar_init(&sm.rec_empty[i], NW); }
-            for (int i = 0; i < NPH; ++i) { mbar_init(&sm.rec_written[i], NW); mbar_init(&sm.pub_done[i], 1); }
+            for (int i = 0; i < NPH; ++i) { mbar_init(&sm.rec_written[i], NW + 1); mbar_init(&sm.pub_done[i], 1); }  // k-groups + feeder
             for (int i = 0; i < NS_OUT; ++i) mbar_init(&sm.out_empty[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
@@ -412,6 +412,11 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
                 if (++in_slot == NS_IN) { in_slot = 0; in_par ^= 1; }
             };
             acquire_in_block();
+            // drain side: output-ring and interval bookkeeping (the storer waits for the k-groups AND this warp)
+            constexpr int ROUT = SM::ROUT;
+            int ro = ((-lane - KB) % ROUT + ROUT) % ROUT;   // ring position of rho_out = t - lane - KB at t = 0
+            int out_slot = 0, out_par = 0;                  // slot / parity of the next output block that reuses a slot
+            int pub_slot = 0, pub_par = 0, jd = 0, sgd = 0; // rec_written / pub_done slot of the interval, interval index, step in it
             for (int tf = -2; tf < T; ++tf) {
                 if (tf + 1 < T) {
                     if (tf + 1 > 0 && ((tf + 1) % RB) == 0) acquire_in_block();
@@ -434,6 +439,33 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
                     rr1 = (rr1 + 1 == RIN) ? 0 : rr1 + 1;
                 }
                 bar_sync_imm<BAR_STEP, NCT + 32>();
+                if (tf >= 0) {
+                    // ---- drain: iteration KB-1 of step tf retired -> final values into the output ring
+                    const int tk = tf - KB;  // lane 0's output row
+                    if (tk >= 0 && (tk % RB) == 0 && tk / RB >= NS_OUT) {  // lane 0 enters a block whose slot was used before:
+                        mbar_wait(&sm.out_empty[out_slot], out_par);      // the storer must have emptied it
+                        if (++out_slot == NS_OUT) { out_slot = 0; out_par ^= 1; }
+                    }
+                    const float4 o = sm.grp[tf & 1][NW][lane];
+                    if (tf - lane - KB >= 0) {
+                        sm.out_u[lane][ro] = o.x;
+                        sm.out_v[lane][ro] = o.y;
+                        sm.out_p[lane][ro] = o.z;
+                    }
+                    ro = (ro + 1 == ROUT) ? 0 : ro + 1;
+                    if (sgd == G - 1 || tf == T - 1) {  // end of a record interval: this warp's part of "steps retired"
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (jd >= NPH) mbar_wait(&sm.pub_done[pub_slot], pub_par ^ 1);
+                            mbar_arrive(&sm.rec_written[pub_slot]);
+                        }
+                        ++jd;
+                        if (++pub_slot == NPH) { pub_slot = 0; pub_par ^= 1; }
+                        sgd = 0;
+                    } else {
+                        ++sgd;
+                    }
+                }
             }
         } else {
             // ================================== compute warps =========================================
@@ -446,15 +478,13 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
 #pragma unroll
             for (int k = 0; k < KG; ++k) uL[k] = uRo[k] = vB[k] = vTo[k] = pin[k] = pd[k] = 0.0f;
             unsigned fl = 0u, fld = 0u;  // KG nibbles: flags used this step / arriving for the step after next
-            constexpr int ROUT = SM::ROUT;
             constexpr unsigned FULL = (KG == 8) ? 0xFFFFFFFFu : ((1u << (4 * KG)) - 1u);
             const bool group_active = (g + 1) * KG <= k_act;  // every iteration of this k-group runs in this pass
             // record-interval bookkeeping (all k-groups) and output-ring bookkeeping (last k-group)
             int rec_slot = 0, rec_par = 0;                  // slot / parity of the interval being consumed
             int pub_slot = 0, pub_par = 0;                  // rec_written / pub_done slot of this interval
             int j = 0;                                      // interval index
-            int ro = ((-lane - KB) % ROUT + ROUT) % ROUT;   // ring position of rho_out = t - lane - KB at t = 0
-            int out_m = NS_OUT, out_slot = 0, out_par = 0;  // next output block whose slot must be free again
+            const bool last_group = g == NW - 1;
             const float4 *rec_base = &sm.rec[0][g][0][0];
             constexpr int REC_SLOT_STRIDE = NW * G * KG;    // float4 per ring slot
 
@@ -477,16 +507,6 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
                 TFS_TR(0)
                 if (sg == 0) {
                     mbar_wait(&sm.rec_full[rec_slot], rec_par);
-                    if (g == NW - 1) {
-                        // lane 0 first touches output block m at step RB*m + KB: if that falls in this
-                        // interval and the slot was used before, the storer must have emptied it
-                        const int first = RB * out_m + KB;
-                        if (first < t + G) {
-                            mbar_wait(&sm.out_empty[out_slot], out_par);
-                            ++out_m;
-                            if (++out_slot == NS_OUT) { out_slot = 0; out_par ^= 1; }
-                        }
-                    }
                 }
                 TFS_TR(6)
                 // ---- early loads: left band's record (for lane 0)
@@ -543,17 +563,11 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
                 }
                 s_flv = (lane == 0) ? __float_as_uint(lr[0].w) : s_flv;
                 TFS_TR(3)
-                // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}
-                sm.grp[t & 1][g + 1][lane] =
-                    make_float4(a[KG - 1], s_v[KG - 1], s_p[KG - 1], __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
-                if (g == NW - 1) {  // iteration KB-1 retired: final values of cell (q-(KB-1), t-lane-KB) -> output ring
-                    if (t - lane - KB >= 0) {
-                        sm.out_u[lane][ro] = a[KG - 1];
-                        sm.out_v[lane][ro] = cv[KG - 1];
-                        sm.out_p[lane][ro] = pp[KG - 1];
-                    }
-                    ro = (ro + 1 == ROUT) ? 0 : ro + 1;
-                }
+                // ---- hand-over to the next k-group: {uCf, lane L-1's vCf, lane L-1's pout, its flags nibble}; the last
+                // k-group hands its own lane's final u, v, p of cell (q-(KB-1), t-lane-KB) to the feeder warp, which
+                // moves them into the output ring (three stores and the ring bookkeeping less in this warp's step)
+                sm.grp[t & 1][g + 1][lane] = make_float4(a[KG - 1], last_group ? cv[KG - 1] : s_v[KG - 1], last_group ? pp[KG - 1] : s_p[KG - 1],
+                                                         __uint_as_float((s_flv >> (4 * (KG - 1))) & 15u));
                 // ---- record of lane 31 for the same k-group of the next band (consumed at the end of ITS step t-32)
                 {
                     const int r_out = t - 32;
