@@ -71,7 +71,7 @@ def is_env(a):
 if __name__ == "__main__":
     env = {a.split("=", 1)[0]: a.split("=", 1)[1] for a in sys.argv[1:] if is_env(a)}
     for spec in [a for a in sys.argv[1:] if not is_env(a)]:
-        if spec == "chain":   # ~1000 cycles per step for one band alone, ~1200 with 3 CTAs/SM
+        if spec == "chain":   # ~830 cycles per step for one band alone, ~1100 with 3 CTAs/SM
             for tag, cfg in (("1 band alone", [16, 262144, 16, 9.8, 0, 3, "none"]),
                              ("128 bands, 1 CTA/SM", [16 + 32 * 127, 32768, 16, 9.8, 0, 3, "none"]),
                              ("128 bands x 3 passes, 3 CTAs/SM", [16 + 32 * 127, 32768, 48, 9.8, 0, 3, "none"])):
