@@ -2,14 +2,17 @@
 //
 // Same schedule and arithmetic as tfs_systolic.cuh (see its header and oracle/systolic_model.py);
 // what changes is how data moves between HBM and the pipeline:
-//   * warp roles: NW compute warps (k-groups), one LOADER warp, one STORER warp.  Every wait on
-//     global memory (progress counters of other CTAs), every fence and every bulk copy lives in the
-//     two IO warps; compute warps only touch registers, shared memory and shared-memory mbarriers.
-//   * k = 0 operands come from rectangular 32-column x 32-row blocks (one 128-byte line per column
-//     and field), copied global -> shared with 16-byte cp.async.cg (bypasses L1: no stale lines)
-//     into a 3-slot ring; lane l reads row tau - l - 1, i.e. bank (tau - l - 1) & 31: conflict-free.
-//   * final values are written into a 3-slot ring of 32 x 32 blocks and stored with 128-bit
-//     coalesced stores once the last lane has retired the block's last row.
+//   * warp roles: NW compute warps (k-groups), one LOADER warp, one STORER warp, one FEEDER warp.  Every
+//     wait on global memory (progress counters of other CTAs), every fence and every bulk copy lives in
+//     the loader and the storer; compute warps only touch registers, shared memory and shared-memory
+//     mbarriers, and all of them execute the same instructions: the feeder warp reads the k = 0 operands
+//     out of the input ring for the first k-group and moves the last k-group's results into the output
+//     ring, both through the k-groups' own hand-over slots and the same per-step named barrier.
+//   * k = 0 operands come from rectangular blocks of 32 columns x RB rows (RB = 16: 4-slot ring, the
+//     shipped form; RB = 32: 3 slots), copied global -> shared with 16-byte cp.async.cg (bypasses L1: no
+//     stale lines); lane l reads row tau - l - 1, i.e. bank (tau - l - 1) & 31: conflict-free.
+//   * final values are written into a ring of the same geometry and stored with 128-bit coalesced
+//     stores once the last lane has retired the block's last row.
 //   * the left band's records are prefetched per interval of G steps (not per chunk), published by
 //     the producer's storer warp every G steps, so a band trails its left neighbour by ~32 + 2G
 //     steps; all hand-offs inside the CTA are mbarrier full/empty pairs.
