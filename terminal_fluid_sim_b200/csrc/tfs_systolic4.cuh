@@ -120,7 +120,7 @@ struct Sys4Smem {
 };
 
 template <int KG, int NW, int G, int RB>
-__global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
+__global__ void __launch_bounds__(32 * (NW + 4), (RB == 16 && NW <= 4 && KG <= 5) ? 3 : (NW <= 4 ? 2 : 1)) k_project_systolic4(Sys4Params P4) {
     using SM = Sys4Smem<KG, NW, G, RB>;
     static_assert(RB == 16 || RB == 32, "ring blocks are 16 or 32 rows");
     static_assert(RB % G == 0, "a ring block is a whole number of record intervals");
@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(32 * (NW + 3), (RB == 16 && NW <= 4 && KG <= 5
 
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const bool is_loader = g == NW, is_storer = g == NW + 1, is_feeder = g == NW + 2;
+    // An eighth, idle warp: the same kernel launched with NW + 3 warps per CTA is 2-5 % slower at every size (one band
+    // alone 111 -> 105 ms for 262144 steps, 4096^2 K=100 6.77 -> 6.45 ms, 32768^2 K=200 674 -> 662 ms), whichever of the
+    // warps NW .. NW+3 is the idle one (all eight assignments of loader / storer / feeder / idle tried gave 6.45-6.49
+    // and 660-664 ms): the warp count of the CTA matters, not which scheduler hosts which helper.
+    if (g == NW + 3) return;
     const long long W = P.W, H = P.H;
     const int n_tasks = P4.n_tasks;
     const Sys4Slab &SL = P4.slab;
@@ -822,7 +827,7 @@ struct Sys4Launch {
                 *msg = "cudaFuncSetAttribute(max dynamic smem)";
                 return e;
             }
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 3), smem)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], kern, 32 * (NW + 4), smem)) != cudaSuccess) return e;
             attr_set[di] = true;
         }
         const int occ = occ_dev[di];
@@ -852,7 +857,7 @@ struct Sys4Launch {
         cudaMemsetAsync(d_tt[di], 0, (size_t)n_tasks * 4 * sizeof(unsigned long long), a.stream);
         P4.ttrace = d_tt[di];
 #endif
-        kern<<<grid, 32 * (NW + 3), smem, a.stream>>>(P4);
+        kern<<<grid, 32 * (NW + 4), smem, a.stream>>>(P4);
         if ((e = cudaGetLastError()) != cudaSuccess) { *msg = "kernel launch"; return e; }
         *launched += 1;
         ws4.last_kg = KG; ws4.last_nw = NW; ws4.last_passes = P.n_passes;
