@@ -183,8 +183,8 @@ def run_ours(args):
     achieved = alg_bytes / (proj_ms / 1e3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of the projection kernel, per launch, from the ncu captures
     # committed under profiles/ (a separate run of the same configuration; never measured inside this timed run)
-    traffic = {("c5", "exact"): (4.715e11, "profiles/r02c_c5_exact_dram.csv"),
-               ("c3", "exact"): (2.388e9, "profiles/r02c_systolic4_c3.txt"),
+    traffic = {("c5", "exact"): (4.699e11, "profiles/r02c_c5_exact_dram.csv"),
+               ("c3", "exact"): (2.246e9, "profiles/r02c_systolic4_c3.txt"),
                ("c5", "rb"): (1.922e12, "profiles/r02b_c5_rb_dram.csv (28.7 GB per pass x 67 passes)"),
                ("c3", "rb"): (1.438e10, "profiles/r02b_rb_c3.txt (0.423 GB per pass x 34 passes)"),
                ("c4", "rb"): (1.231e11, "profiles/r02b_rb_c4.txt (7.24 GB per pass x 17 passes)")}.get((args.workload, args.mode), (None, None))
