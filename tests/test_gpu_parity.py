@@ -90,6 +90,21 @@ def test_random_obstacles_and_fields_bit_exact(W, H, K, tb, kernel):
         assert_same(g, o, f"{W}x{H} K={K} step {st}")
 
 
+@pytest.mark.parametrize("W,H,K", [(33, 4, 5), (8, 8, 20), (100, 12, 16), (5, 16, 50), (64, 20, 17), (3, 4, 1), (200, 24, 33)])
+def test_systolic_kernel_on_short_columns_bit_exact(W, H, K):
+    """The block-ring systolic kernel (H % 4 == 0) forced onto grids whose columns are shorter than one ring block or than
+    the 32-lane skew: the feeder warp's priming rounds, the first / last ring block and the record intervals all degenerate."""
+    g, o = make_pair(W, H, gravity=-3.0, iterations=K, kernel=tfs.KERNEL_SYSTOLIC)
+    skip_if_unavailable(tfs.FluidSim(8, 8, kernel=tfs.KERNEL_SYSTOLIC), tfs.KERNEL_SYSTOLIC)
+    thr = frac_to_threshold(0.1)
+    g.scene_random(W * 7 + H, thr); o.L.orc_scene_random(o.h, W * 7 + H, thr)
+    g.fill_random_velocity(5, 25.0); o.fill_random_velocity(5, 25.0)
+    for st in range(3):
+        g.next_step(DT); o.step(DT)
+        assert_same(g, o, f"{W}x{H} K={K} step {st}")
+    assert g.last_projection()["kernel"] in (tfs.PROJ_SYSTOLIC_BLOCK_RING, tfs.PROJ_NONE)
+
+
 def test_config2_wind_tunnel_1024_bit_exact():
     """BASELINE config 2: 1024^2 wind tunnel, disc obstacle, K=40."""
     g, o = make_pair(1024, 1024, iterations=40)
