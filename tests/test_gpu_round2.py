@@ -186,6 +186,21 @@ def test_redblack_fused_bit_exact_vs_its_cpu_statement(W, H, K, grav, frac):
     assert_same(g, o, "phase_project", "uvp")
 
 
+@pytest.mark.parametrize("W,H,K", [(3, 2, 1), (13, 4, 3), (12, 52, 4), (25, 50, 7), (97, 54, 2), (127, 104, 5), (253, 106, 3),
+                                   (126, 52, 6), (5, 208, 4)])
+def test_redblack_tiled_kernel_at_strip_and_chunk_boundaries(W, H, K):
+    """k_project_rb itself (options.kernel = SYSTOLIC keeps the one-CTA kernel out) on grids whose height sits at the
+    edges of its 52-row strips and whose width at the edges of its 12 ... 126-column chunks; K around the 3 fused iterations."""
+    g = tfs.FluidSim(W, H, tfs.SimConfig(gravity=1.5), iterations=K, mode=tfs.MODE_RED_BLACK, kernel=tfs.KERNEL_SYSTOLIC)
+    o = OracleSim(W, H, gravity=1.5, iterations=K, mode=1)
+    g.scene_random(W * 3 + H, frac_to_threshold(0.07)); o.scene_random(W * 3 + H, 0.07)
+    g.fill_random_velocity(8, 30.0); o.fill_random_velocity(8, 30.0)
+    for st in range(3):
+        g.next_step(DT); o.step(DT)
+        assert g.last_projection()["kernel"] == tfs.PROJ_REDBLACK_FUSED
+        assert_same(g, o, f"red-black {W}x{H} K={K} step {st}")
+
+
 def test_redblack_odd_height_takes_the_simple_kernel_and_is_exact_too():
     g = tfs.FluidSim(190, 97, iterations=11, mode=tfs.MODE_RED_BLACK)
     o = OracleSim(190, 97, iterations=11, mode=1)
